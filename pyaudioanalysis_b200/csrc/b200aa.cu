@@ -1,0 +1,757 @@
+// libb200aa.so -- C ABI (include/b200aa.h) over the sm_100a kernels.
+// Build: see pyaudioanalysis_b200/build.py (nvcc -gencode arch=compute_100a,code=sm_100a).
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200aa.h"
+#include "common.cuh"
+#include "generic_kernel.cuh"
+#include "fast_kernel.cuh"
+#include "tables.inl"
+
+using namespace b200aa;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_cuda_err;
+static std::atomic<int64_t> g_launches{0};
+
+static int cuda_fail(cudaError_t e, const char *what)
+{
+    g_cuda_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return B200AA_ERR_CUDA;
+}
+#define CK(call)                                                     \
+    do {                                                             \
+        cudaError_t e_ = (call);                                     \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);          \
+    } while (0)
+#define CK_LAUNCH(name)                                              \
+    do {                                                             \
+        g_launches.fetch_add(1, std::memory_order_relaxed);          \
+        cudaError_t e_ = cudaGetLastError();                         \
+        if (e_ != cudaSuccess) return cuda_fail(e_, name);           \
+    } while (0)
+
+extern "C" int b200aa_abi_version(void) { return B200AA_ABI_VERSION; }
+extern "C" int64_t b200aa_launch_count(void) { return g_launches.load(); }
+extern "C" const char *b200aa_last_cuda_error(void) { return g_cuda_err.c_str(); }
+
+extern "C" const char *b200aa_status_string(int s)
+{
+    switch (s) {
+    case B200AA_OK: return "ok";
+    case B200AA_ERR_INVALID: return "invalid argument";
+    case B200AA_ERR_TOO_SHORT: return "need at least one array to concatenate";   // the reference's text
+    case B200AA_ERR_CHROMA: return "chroma: semitone index >= num_fft (window too short for this sampling rate)";
+    case B200AA_ERR_MEL_RANGE: return "mel filterbank: filter edge beyond num_fft";
+    case B200AA_ERR_CUDA: return "CUDA error";
+    case B200AA_ERR_UNSUPPORTED: return "window too large for the on-chip transform";
+    case B200AA_ERR_NO_DEVICE: return "no sm_100 CUDA device";
+    default: return "unknown status";
+    }
+}
+
+extern "C" int b200aa_device_ok(void)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return B200AA_ERR_NO_DEVICE; }
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, dev) != cudaSuccess) { cudaGetLastError(); return B200AA_ERR_NO_DEVICE; }
+    return pr.major == 10 ? B200AA_OK : B200AA_ERR_NO_DEVICE;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host tables / counts
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200aa_host_table(int fs, int window, int which, double *h_out)
+{
+    if (!h_out || window < 2 || fs <= 0) return B200AA_ERR_INVALID;
+    const int K = window / 2;
+    std::vector<double> t;
+    int rc = B200AA_OK;
+    if (which == 0) rc = b200aa_host::build_mel(fs, K, t);
+    else if (which == 1) rc = b200aa_host::build_chroma(fs, K, t);
+    else if (which == 2) b200aa_host::build_dct(t);
+    else return B200AA_ERR_INVALID;
+    if (rc != B200AA_OK) return rc;
+    std::memcpy(h_out, t.data(), t.size() * sizeof(double));
+    return B200AA_OK;
+}
+
+extern "C" int64_t b200aa_num_frames(int64_t n, int w, int s)
+{
+    return (w < 1 || s < 1) ? 0 : b200aa_host::num_frames(n, w, s);
+}
+extern "C" int64_t b200aa_spectrogram_rows(int64_t n, int w, int s)
+{
+    if (w < 1 || s < 1) return 0;
+    // int((N - w) / s) + 1 with Python's truncation toward zero (ShortTermFeatures.py:413)
+    return (n - w) / s + 1;
+}
+extern "C" int64_t b200aa_chromagram_rows(int64_t n, int w, int s)
+{
+    if (w < 1 || s < 1) return 0;
+    return (n - s - w) / s + 1;     // C division truncates toward zero like int(x / y) (:347)
+}
+extern "C" int64_t b200aa_mid_windows(int64_t n_frames, int stepr)
+{
+    return (stepr < 1 || n_frames <= 0) ? 0 : (n_frames + stepr - 1) / stepr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+struct Transform {           // device tables of one transform length
+    int n = 0, Nc = 0, packed = 0;
+    std::vector<int> radix;
+    float2 *d_tw = nullptr, *d_tw_post = nullptr;
+    ~Transform()
+    {
+        if (d_tw) cudaFree(d_tw);
+        if (d_tw_post) cudaFree(d_tw_post);
+    }
+};
+
+struct b200aa_plan {
+    int fs = 0, window = 0, step = 0, K = 0;
+    int device = 0, sm_count = 0;
+    int force_generic = 0;
+    int fast_kind = 0;                  // 0 = none, else index of the specialised kernel
+    BlobLayout bl{};
+    int *d_blob = nullptr;
+    std::vector<int> h_blob;
+    std::mutex mu;
+    std::map<int, std::unique_ptr<Transform>> transforms;   // by transform length
+    FastTables fast{};                  // extra device tables of the specialised kernel
+    ~b200aa_plan()
+    {
+        if (d_blob) cudaFree(d_blob);
+        fast.release();
+    }
+};
+
+static int make_transform(int n, std::unique_ptr<Transform> &out)
+{
+    std::unique_ptr<Transform> t(new Transform);
+    t->n = n;
+    t->packed = (n % 2 == 0) ? 1 : 0;
+    t->Nc = t->packed ? n / 2 : n;
+    t->radix = b200aa_host::radix_list(t->Nc);
+    if (t->Nc == 1) t->radix.clear();
+    if ((int)t->radix.size() > kMaxRadix) return B200AA_ERR_UNSUPPORTED;
+    std::vector<float2> tw(t->Nc), tp(t->Nc);
+    for (int j = 0; j < t->Nc; ++j) {
+        const double a = -2.0 * b200aa_host::kPi * double(j) / double(t->Nc);
+        tw[j] = make_float2(float(std::cos(a)), float(std::sin(a)));
+        const double b = -2.0 * b200aa_host::kPi * double(j) / double(n);
+        tp[j] = make_float2(float(std::cos(b)), float(std::sin(b)));
+    }
+    CK(cudaMalloc(&t->d_tw, sizeof(float2) * t->Nc));
+    CK(cudaMalloc(&t->d_tw_post, sizeof(float2) * t->Nc));
+    CK(cudaMemcpy(t->d_tw, tw.data(), sizeof(float2) * t->Nc, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(t->d_tw_post, tp.data(), sizeof(float2) * t->Nc, cudaMemcpyHostToDevice));
+    out = std::move(t);
+    return B200AA_OK;
+}
+
+static int get_transform(b200aa_plan *pl, int n, Transform **out)
+{
+    std::lock_guard<std::mutex> g(pl->mu);
+    auto it = pl->transforms.find(n);
+    if (it == pl->transforms.end()) {
+        std::unique_ptr<Transform> t;
+        int rc = make_transform(n, t);
+        if (rc != B200AA_OK) return rc;
+        it = pl->transforms.emplace(n, std::move(t)).first;
+    }
+    *out = it->second.get();
+    return B200AA_OK;
+}
+
+// pack mel CSR + DCT + chroma entries into one int32 blob
+static int build_blob(int fs, int K, std::vector<int> &blob, BlobLayout &bl, bool need_features)
+{
+    std::vector<double> mel, chr, dct;
+    int rc_mel = b200aa_host::build_mel(fs, K, mel);
+    int rc_chr = b200aa_host::build_chroma(fs, K, chr);
+    if (need_features) {
+        if (rc_chr != B200AA_OK) return rc_chr;    // the reference fails in chroma_features on frame 0 ...
+        if (rc_mel != B200AA_OK) return rc_mel;    // ... or earlier in mfcc_filter_banks
+    }
+    b200aa_host::build_dct(dct);
+    std::vector<int> m_start(40, 0), m_count(40, 0), m_off(40, 0);
+    std::vector<float> m_w;
+    if (rc_mel == B200AA_OK)
+        for (int i = 0; i < 40; ++i) {
+            int lo = -1, hi = -1;
+            for (int k = 0; k < K; ++k)
+                if (mel[size_t(i) * K + k] != 0.0) { if (lo < 0) lo = k; hi = k; }
+            m_off[i] = (int)m_w.size();
+            if (lo >= 0) {
+                m_start[i] = lo;
+                m_count[i] = hi - lo + 1;
+                for (int k = lo; k <= hi; ++k) m_w.push_back(float(mel[size_t(i) * K + k]));
+            }
+        }
+    std::vector<int> c_off(13, 0), c_bin;
+    std::vector<float> c_w;
+    if (rc_chr == B200AA_OK)
+        for (int c = 0; c < 12; ++c) {
+            c_off[c] = (int)c_bin.size();
+            for (int k = 0; k < K; ++k)
+                if (chr[size_t(c) * K + k] != 0.0) { c_bin.push_back(k); c_w.push_back(float(chr[size_t(c) * K + k])); }
+            c_off[c + 1] = (int)c_bin.size();
+        }
+    auto put_i = [&](const std::vector<int> &v) { int at = (int)blob.size(); blob.insert(blob.end(), v.begin(), v.end()); return at; };
+    auto put_f = [&](const std::vector<float> &v) {
+        int at = (int)blob.size();
+        for (float f : v) { int w; std::memcpy(&w, &f, 4); blob.push_back(w); }
+        return at;
+    };
+    blob.clear();
+    bl.mel_start = put_i(m_start);
+    bl.mel_count = put_i(m_count);
+    bl.mel_off = put_i(m_off);
+    bl.mel_w = put_f(m_w);
+    std::vector<float> dpad(13 * 41, 0.f);
+    for (int r = 0; r < 13; ++r)
+        for (int n = 0; n < 40; ++n) dpad[r * 41 + n] = float(dct[size_t(r) * 40 + n]);
+    bl.dct = put_f(dpad);
+    bl.chr_off = put_i(c_off);
+    bl.chr_bin = put_i(c_bin);
+    bl.chr_w = put_f(c_w);
+    while (blob.size() % 4) blob.push_back(0);
+    bl.words = (int)blob.size();
+    return (rc_chr != B200AA_OK) ? rc_chr : rc_mel;
+}
+
+extern "C" int b200aa_plan_create(b200aa_plan **out, int fs, int window, int step)
+{
+    if (!out || fs <= 0 || window < 2 || step < 1) return B200AA_ERR_INVALID;
+    int rc = b200aa_device_ok();
+    if (rc != B200AA_OK) return rc;
+    std::unique_ptr<b200aa_plan> pl(new b200aa_plan);
+    pl->fs = fs; pl->window = window; pl->step = step; pl->K = window / 2;
+    CK(cudaGetDevice(&pl->device));
+    CK(cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, pl->device));
+    // tables that only feature_extraction / chromagram need may be unbuildable (the reference raises
+    // there too); spectrogram must still work, so remember the status instead of failing here.
+    int trc = build_blob(fs, pl->K, pl->h_blob, pl->bl, false);
+    (void)trc;
+    CK(cudaMalloc(&pl->d_blob, sizeof(int) * pl->h_blob.size()));
+    CK(cudaMemcpy(pl->d_blob, pl->h_blob.data(), sizeof(int) * pl->h_blob.size(), cudaMemcpyHostToDevice));
+    Transform *t = nullptr;
+    rc = get_transform(pl.get(), window, &t);
+    if (rc != B200AA_OK) return rc;
+    rc = fast_plan_init(fs, window, step, pl->h_blob, pl->bl, &pl->fast, &pl->fast_kind);
+    if (rc != B200AA_OK) return rc;
+    *out = pl.release();
+    return B200AA_OK;
+}
+
+extern "C" void b200aa_plan_destroy(b200aa_plan *plan) { delete plan; }
+extern "C" int b200aa_plan_kernel_kind(const b200aa_plan *plan)
+{
+    return (plan && plan->fast_kind && !plan->force_generic) ? 1 : 0;
+}
+extern "C" int b200aa_plan_force_generic(b200aa_plan *plan, int on)
+{
+    if (!plan) return 0;
+    int prev = plan->force_generic;
+    plan->force_generic = on ? 1 : 0;
+    return prev;
+}
+
+// feature tables status (chroma / mel buildable?) -- recomputed cheaply on the host
+static int feature_tables_status(const b200aa_plan *pl)
+{
+    std::vector<double> t;
+    int rc = b200aa_host::build_chroma(pl->fs, pl->K, t);
+    if (rc != B200AA_OK) return rc;
+    return b200aa_host::build_mel(pl->fs, pl->K, t);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 0: clip statistics  (signal / 2**15 + dc_normalize, ShortTermFeatures.py:567-570, :14-19)
+// accumulators live in the output records: rsv[0..1] = sum (int64 / double), lo/hi = min/max keys
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int float_key(float f)
+{
+    int b = __float_as_int(f);
+    return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+__global__ void stats_init_kernel(b200aa_clip_norm *nm, int64_t n)
+{
+    int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long *acc = reinterpret_cast<unsigned long long *>(&nm[i].rsv[0]);
+    *acc = 0ull;
+    reinterpret_cast<int *>(&nm[i].lo)[0] = 0x7fffffff;              // running min key
+    reinterpret_cast<int *>(&nm[i].hi)[0] = int(0x80000000u);        // running max key
+}
+
+template <int DTYPE>
+__global__ void __launch_bounds__(256) stats_accum_kernel(const void *sig, int64_t n_samples, int64_t clip_stride,
+                                                           const int64_t *len, b200aa_clip_norm *nm, int chunks)
+{
+    const int64_t b = blockIdx.y;
+    const int64_t L = len ? len[b] : n_samples;
+    const int64_t per = (L + chunks - 1) / chunks;
+    const int64_t s0 = blockIdx.x * per, s1 = min(L, s0 + per);
+    long long isum = 0;
+    double dsum = 0.0;
+    int kmin = 0x7fffffff, kmax = int(0x80000000u);
+    if (DTYPE == B200AA_DTYPE_I16) {
+        const short *x = reinterpret_cast<const short *>(sig) + b * clip_stride;
+        int mn = 32767, mx = -32768;
+        int64_t i = s0 + threadIdx.x;
+        // 16-byte vector body when the chunk start is aligned
+        const bool al = ((reinterpret_cast<uintptr_t>(x + s0) & 15) == 0);
+        if (al) {
+            const int4 *v = reinterpret_cast<const int4 *>(x + s0);
+            const int64_t nv = (s1 - s0) / 8;
+            for (int64_t j = threadIdx.x; j < nv; j += blockDim.x) {
+                int acc = 0;
+                const int4 q = __ldg(v + j);
+                const int w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int a0 = (short)(w4[u] & 0xffff), a1 = w4[u] >> 16;
+                    acc += a0 + a1;
+                    mn = min(mn, min(a0, a1));
+                    mx = max(mx, max(a0, a1));
+                }
+                isum += acc;
+            }
+            i = s0 + nv * 8 + threadIdx.x;
+        }
+        for (; i < s1; i += blockDim.x) {
+            const int a0 = x[i];
+            isum += a0;
+            mn = min(mn, a0);
+            mx = max(mx, a0);
+        }
+        kmin = mn; kmax = mx;
+    } else {
+        const float *x = reinterpret_cast<const float *>(sig) + b * clip_stride;
+        for (int64_t i = s0 + threadIdx.x; i < s1; i += blockDim.x) {
+            const float v = x[i];
+            dsum += double(v);
+            const int k = float_key(v);
+            kmin = min(kmin, k);
+            kmax = max(kmax, k);
+        }
+    }
+    // block reduce
+    __shared__ long long s_i[8];
+    __shared__ double s_d[8];
+    __shared__ int s_mn[8], s_mx[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        isum += __shfl_xor_sync(0xffffffffu, isum, o);
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if (lane == 0) { s_i[warp] = isum; s_d[warp] = dsum; s_mn[warp] = kmin; s_mx[warp] = kmax; }
+    __syncthreads();
+    if (threadIdx.x == 0 && s1 > s0) {
+        for (int w = 1; w < 8; ++w) { isum += s_i[w]; dsum += s_d[w]; kmin = min(kmin, s_mn[w]); kmax = max(kmax, s_mx[w]); }
+        if (DTYPE == B200AA_DTYPE_I16)
+            atomicAdd(reinterpret_cast<unsigned long long *>(&nm[b].rsv[0]), (unsigned long long)isum);
+        else
+            atomicAdd(reinterpret_cast<double *>(&nm[b].rsv[0]), dsum);
+        atomicMin(reinterpret_cast<int *>(&nm[b].lo), kmin);
+        atomicMax(reinterpret_cast<int *>(&nm[b].hi), kmax);
+    }
+}
+
+template <int DTYPE>
+__global__ void stats_finish_kernel(b200aa_clip_norm *nm, int64_t n, int64_t n_samples, const int64_t *len)
+{
+    int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    const int64_t L = len ? len[i] : n_samples;
+    b200aa_clip_norm r = nm[i];
+    double mean, mn, mx;
+    if (DTYPE == B200AA_DTYPE_I16) {
+        const long long s = *reinterpret_cast<const long long *>(&r.rsv[0]);
+        mean = L > 0 ? double(s) / double(L) : 0.0;
+        mn = double(*reinterpret_cast<const int *>(&r.lo));
+        mx = double(*reinterpret_cast<const int *>(&r.hi));
+    } else {
+        const double s = *reinterpret_cast<const double *>(&r.rsv[0]);
+        mean = L > 0 ? s / double(L) : 0.0;
+        mn = double(key_float(*reinterpret_cast<const int *>(&r.lo)));
+        mx = double(key_float(*reinterpret_cast<const int *>(&r.hi)));
+    }
+    if (L <= 0) { mn = mx = 0.0; }
+    // y = (x/2^15 - mean/2^15) / (max|x/2^15 - mean/2^15| + 1e-10)  ==  (x - mean) / (maxdev + 2^15 * 1e-10)
+    const double maxdev = fmax(mx - mean, mean - mn);
+    const double a = 1.0 / (maxdev + 32768.0 * 1e-10);
+    double m, lo, hi;
+    if (DTYPE == B200AA_DTYPE_I16) {
+        m = nearbyint(mean);
+        lo = floor(mean);
+        hi = ceil(mean);
+    } else {
+        const float mf = float(mean);
+        m = double(mf);
+        if (double(mf) > mean) { hi = mf; lo = nextafterf(mf, -INFINITY); }
+        else if (double(mf) < mean) { lo = mf; hi = nextafterf(mf, INFINITY); }
+        else { lo = hi = mf; }
+    }
+    b200aa_clip_norm o;
+    o.a = float(a);
+    o.bp = float(a * (m - mean));
+    o.m = float(m);
+    o.lo = float(lo - m);
+    o.hi = float(hi - m);
+    o.rsv[0] = o.rsv[1] = o.rsv[2] = 0.f;
+    nm[i] = o;
+}
+
+extern "C" int b200aa_clip_stats(const void *d_sig, int dtype, int64_t n_clips, int64_t n_samples,
+                                 int64_t clip_stride, const int64_t *d_len, b200aa_clip_norm *d_norm, void *stream)
+{
+    if (!d_sig || !d_norm || n_clips < 0 || n_samples < 0 || (dtype != 0 && dtype != 1)) return B200AA_ERR_INVALID;
+    if (n_clips == 0) return B200AA_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int dev = 0, sms = 148;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int tb = 256;
+    stats_init_kernel<<<(unsigned)((n_clips + tb - 1) / tb), tb, 0, st>>>(d_norm, n_clips);
+    CK_LAUNCH("stats_init_kernel");
+    // enough CTAs to fill the machine, each reading >= 32 KiB
+    int64_t want = (int64_t(sms) * 8 + n_clips - 1) / n_clips;
+    const int64_t bytes = n_samples * (dtype == 0 ? 2 : 4);
+    int64_t cap = (bytes + 32767) / 32768;
+    int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(want, cap));
+    for (int64_t b0 = 0; b0 < n_clips; b0 += 32768) {
+        const int64_t nb = std::min<int64_t>(32768, n_clips - b0);
+        dim3 grid(chunks, (unsigned)nb);
+        const size_t es = dtype == 0 ? 2 : 4;
+        const void *sig = reinterpret_cast<const char *>(d_sig) + size_t(b0) * clip_stride * es;
+        const int64_t *ln = d_len ? d_len + b0 : nullptr;
+        if (dtype == 0) stats_accum_kernel<0><<<grid, 256, 0, st>>>(sig, n_samples, clip_stride, ln, d_norm + b0, chunks);
+        else stats_accum_kernel<1><<<grid, 256, 0, st>>>(sig, n_samples, clip_stride, ln, d_norm + b0, chunks);
+        CK_LAUNCH("stats_accum_kernel");
+    }
+    if (dtype == 0) stats_finish_kernel<0><<<(unsigned)((n_clips + tb - 1) / tb), tb, 0, st>>>(d_norm, n_clips, n_samples, d_len);
+    else stats_finish_kernel<1><<<(unsigned)((n_clips + tb - 1) / tb), tb, 0, st>>>(d_norm, n_clips, n_samples, d_len);
+    CK_LAUNCH("stats_finish_kernel");
+    return B200AA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 2: mid-term pooling (MidTermFeatures.py:110-126): one warp per (clip, feature row, window)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mid_pool_kernel(const float *st, int64_t n_clips, int F, int64_t T,
+                                                        int64_t t_stride, int ratio, int stepr, int64_t M, float *mid)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+    const int64_t total = n_clips * F * M;
+    if (wid >= total) return;
+    const int64_t j = wid % M, bf = wid / M;
+    const int64_t b = bf / F;
+    const int f = int(bf - b * F);
+    const int64_t c0 = j * stepr, c1 = min(T, c0 + ratio);
+    const float *row = st + (size_t(b) * F + f) * t_stride;
+    const int n = int(c1 - c0);
+    double s = 0.0;
+    for (int64_t c = c0 + lane; c < c1; c += 32) s += double(row[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const double mean = s / double(n);
+    double v = 0.0;
+    for (int64_t c = c0 + lane; c < c1; c += 32) { const double d = double(row[c]) - mean; v += d * d; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) {
+        float mu = float(mean), sd = float(sqrt(v / double(n)));
+        // np.nan_to_num (:126)
+        if (isnan(mu)) mu = 0.f;
+        if (isnan(sd)) sd = 0.f;
+        if (isinf(mu)) mu = mu > 0 ? 3.4028234664e38f : -3.4028234664e38f;
+        if (isinf(sd)) sd = 3.4028234664e38f;
+        mid[(size_t(b) * 2 * F + f) * M + j] = mu;
+        mid[(size_t(b) * 2 * F + F + f) * M + j] = sd;
+    }
+}
+
+extern "C" int b200aa_mid_pool(const float *d_st, int64_t n_clips, int n_feats, int64_t n_frames, int64_t t_stride,
+                               int ratio, int step_ratio, float *d_mid, void *stream)
+{
+    if (!d_st || !d_mid || n_clips < 0 || n_feats < 1 || n_frames < 1 || ratio < 1 || step_ratio < 1 || t_stride < n_frames)
+        return B200AA_ERR_INVALID;
+    const int64_t M = b200aa_mid_windows(n_frames, step_ratio);
+    const int64_t warps = n_clips * n_feats * M;
+    if (warps == 0) return B200AA_OK;
+    const int64_t blocks = (warps * 32 + 255) / 256;
+    mid_pool_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_st, n_clips, n_feats, n_frames, t_stride,
+                                                                                       ratio, step_ratio, M, d_mid);
+    CK_LAUNCH("mid_pool_kernel");
+    return B200AA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 1 launchers
+// ------------------------------------------------------------------------------------------------
+static void fill_common(StParams &p, const b200aa_plan *pl, const Transform *t, const void *d_sig, int dtype,
+                        int64_t n_clips, int64_t n_samples, int64_t clip_stride, const int64_t *d_len,
+                        const b200aa_clip_norm *d_norm, float *d_out)
+{
+    std::memset(&p, 0, sizeof(p));
+    p.sig = d_sig; p.len = d_len; p.norm = d_norm; p.out = d_out;
+    p.tw = t->d_tw; p.tw_post = t->d_tw_post; p.blob = pl->d_blob; p.bl = pl->bl;
+    p.n_clips = n_clips; p.n_samples = n_samples; p.clip_stride = clip_stride;
+    p.dtype = dtype; p.window = pl->window; p.fft_n = t->n; p.step = pl->step; p.K = pl->K;
+    p.Kp = (pl->K + 3) & ~3;
+    p.Nc = t->Nc; p.packed = t->packed;
+    p.nrad = (int)t->radix.size();
+    for (int i = 0; i < p.nrad; ++i) p.radix[i] = t->radix[i];
+}
+
+// choose frames/group and launch the generic kernel
+template <int MODE>
+static int launch_generic(const b200aa_plan *pl, StParams &p, int64_t rows_max, cudaStream_t st)
+{
+    int G = 8;
+    size_t smem = 0;
+    for (; G >= 1; G >>= 1) {
+        smem = generic_smem_bytes(G, p.Nc, p.Kp, p.bl.words);
+        if (smem <= (G == 8 ? 100u * 1024u : 220u * 1024u)) break;
+    }
+    if (G < 1) return B200AA_ERR_UNSUPPORTED;
+    p.G = G;
+    // segments: long enough to amortise the 2-frame halo, short enough to balance the SMs
+    int64_t seg = rows_max;
+    if (MODE == kModeFeatures) {
+        const int64_t slots = int64_t(pl->sm_count) * 2;
+        int64_t per_clip = std::max<int64_t>(1, (slots * 12 + p.n_clips - 1) / p.n_clips);
+        seg = std::max<int64_t>(G * 6 - 2, (rows_max + per_clip - 1) / per_clip);
+        seg = std::min<int64_t>(seg, std::max<int64_t>(rows_max, 1));
+    } else {
+        seg = std::max<int64_t>(G * 4, (rows_max + 63) / 64);
+    }
+    p.seg_len = seg;
+    p.segs_per_clip = std::max<int64_t>(1, (rows_max + seg - 1) / seg);
+    p.n_items = p.segs_per_clip * p.n_clips;
+    auto kern = st_generic_kernel<MODE>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
+    occ = std::max(1, occ);
+    const int64_t grid = std::min<int64_t>(p.n_items, int64_t(pl->sm_count) * occ);
+    if (grid == 0) return B200AA_OK;
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(p);
+    CK_LAUNCH("st_generic_kernel");
+    return B200AA_OK;
+}
+
+extern "C" int b200aa_st_features(const b200aa_plan *plan, const void *d_sig, int dtype, int64_t n_clips,
+                                  int64_t n_samples, int64_t clip_stride, const int64_t *d_len,
+                                  const b200aa_clip_norm *d_norm, int deltas, float *d_out, int64_t t_stride, void *stream)
+{
+    if (!plan || !d_sig || !d_norm || !d_out || n_clips < 0 || (dtype != 0 && dtype != 1) || clip_stride < n_samples)
+        return B200AA_ERR_INVALID;
+    b200aa_plan *pl = const_cast<b200aa_plan *>(plan);
+    int rc = feature_tables_status(pl);
+    if (rc != B200AA_OK) return rc;
+    const int64_t T = b200aa_host::num_frames(n_samples, pl->window, pl->step);
+    if (T == 0) return B200AA_ERR_TOO_SHORT;
+    if (t_stride < T) return B200AA_ERR_INVALID;
+    if (n_clips == 0) return B200AA_OK;
+    Transform *t = nullptr;
+    rc = get_transform(pl, pl->window, &t);
+    if (rc != B200AA_OK) return rc;
+    StParams p;
+    fill_common(p, pl, t, d_sig, dtype, n_clips, n_samples, clip_stride, d_len, d_norm, d_out);
+    p.t_stride = t_stride; p.deltas = deltas ? 1 : 0; p.n_out = deltas ? 68 : 34; p.mode = kModeFeatures;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (pl->fast_kind && !pl->force_generic) {
+        rc = fast_launch_features(pl->fast_kind, pl->fast, p, pl->sm_count, T, st);
+        if (rc == B200AA_OK) { g_launches.fetch_add(1, std::memory_order_relaxed); return rc; }
+        if (rc != B200AA_ERR_UNSUPPORTED) return rc == B200AA_ERR_CUDA ? cuda_fail(cudaGetLastError(), "fast kernel") : rc;
+    }
+    return launch_generic<kModeFeatures>(pl, p, T, st);
+}
+
+extern "C" int b200aa_spectrogram(const b200aa_plan *plan, const void *d_sig, int dtype, int64_t n_clips,
+                                  int64_t n_samples, int64_t clip_stride, const b200aa_clip_norm *d_norm,
+                                  float *d_out, void *stream)
+{
+    if (!plan || !d_sig || !d_norm || !d_out || n_clips < 0 || (dtype != 0 && dtype != 1) || clip_stride < n_samples)
+        return B200AA_ERR_INVALID;
+    b200aa_plan *pl = const_cast<b200aa_plan *>(plan);
+    const int w = pl->window, s = pl->step;
+    const int64_t R = b200aa_spectrogram_rows(n_samples, w, s);
+    if (R <= 0) return B200AA_ERR_TOO_SHORT;      // np.zeros with a non-positive row count / empty result
+    if (n_clips == 0) return B200AA_OK;
+    Transform *t = nullptr;
+    int rc = get_transform(pl, w, &t);
+    if (rc != B200AA_OK) return rc;
+    StParams p;
+    fill_common(p, pl, t, d_sig, dtype, n_clips, n_samples, clip_stride, nullptr, d_norm, d_out);
+    p.mode = kModeSpectrogram;
+    p.origin = w; p.row0 = 0; p.rows_total = R; p.rows_launch = R;
+    p.rows_valid = std::min<int64_t>(R, b200aa_host::range_len(w, n_samples - w + 1, s));   // :415
+    return launch_generic<kModeSpectrogram>(pl, p, R, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200aa_chromagram(const b200aa_plan *plan, const void *d_sig, int dtype, int64_t n_clips,
+                                 int64_t n_samples, int64_t clip_stride, const b200aa_clip_norm *d_norm,
+                                 float *d_out, void *stream)
+{
+    if (!plan || !d_sig || !d_norm || !d_out || n_clips < 0 || (dtype != 0 && dtype != 1) || clip_stride < n_samples)
+        return B200AA_ERR_INVALID;
+    b200aa_plan *pl = const_cast<b200aa_plan *>(plan);
+    const int w = pl->window, s = pl->step;
+    const int64_t R = b200aa_chromagram_rows(n_samples, w, s);
+    if (R <= 0 || n_samples - s - w < 0) return B200AA_ERR_TOO_SHORT;
+    int rc = feature_tables_status(pl);
+    if (rc == B200AA_ERR_CHROMA) return rc;
+    if (n_clips == 0) return B200AA_OK;
+    const int64_t n_it = std::min<int64_t>(R, b200aa_host::range_len(w, n_samples - s, s));        // :349
+    // frames that fit entirely: start p = w + i*s with p + w <= N
+    int64_t n_full = 0;
+    if (n_samples - 2 * int64_t(w) >= 0) n_full = std::min<int64_t>(n_it, (n_samples - 2 * int64_t(w)) / s + 1);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Transform *t = nullptr;
+    rc = get_transform(pl, w, &t);
+    if (rc != B200AA_OK) return rc;
+    StParams p;
+    fill_common(p, pl, t, d_sig, dtype, n_clips, n_samples, clip_stride, nullptr, d_norm, d_out);
+    p.mode = kModeChromagram;
+    p.origin = w; p.row0 = 0; p.rows_total = R; p.rows_launch = R; p.rows_valid = n_full;
+    rc = launch_generic<kModeChromagram>(pl, p, R, st);
+    if (rc != B200AA_OK) return rc;
+    // frames clipped at the end of the clip: the reference transforms the n < w samples that are
+    // left (ShortTermFeatures.py:352-355); fewer than num_fft samples make its scatter raise.
+    for (int64_t i = n_full; i < n_it; ++i) {
+        const int64_t start = w + i * s;
+        const int64_t n = n_samples - start;
+        if (n < pl->K) return B200AA_ERR_INVALID;
+        Transform *tc = nullptr;
+        rc = get_transform(pl, (int)n, &tc);
+        if (rc != B200AA_OK) return rc;
+        StParams q;
+        fill_common(q, pl, tc, d_sig, dtype, n_clips, n_samples, clip_stride, nullptr, d_norm, d_out);
+        q.mode = kModeChromagram;
+        q.origin = start; q.row0 = i; q.rows_total = R; q.rows_launch = 1; q.rows_valid = 1;
+        rc = launch_generic<kModeChromagram>(pl, q, 1, st);
+        if (rc != B200AA_OK) return rc;
+    }
+    return B200AA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer entry points
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t n) { return cudaMalloc(&p, n ? n : 1) == cudaSuccess ? 0 : -1; }
+};
+
+extern "C" int b200aa_st_features_host(const b200aa_plan *plan, const void *h_sig, int dtype, int64_t n_clips,
+                                       int64_t n_samples, int deltas, float *h_out)
+{
+    if (!plan || !h_sig || !h_out || n_clips < 1 || (dtype != 0 && dtype != 1)) return B200AA_ERR_INVALID;
+    const int64_t T = b200aa_host::num_frames(n_samples, plan->window, plan->step);
+    if (T == 0) return B200AA_ERR_TOO_SHORT;
+    const int F = deltas ? 68 : 34;
+    const size_t in_b = size_t(n_clips) * n_samples * (dtype == 0 ? 2 : 4), out_b = size_t(n_clips) * F * T * 4;
+    DevBuf sig, nm, out;
+    if (sig.alloc(in_b) || nm.alloc(sizeof(b200aa_clip_norm) * n_clips) || out.alloc(out_b))
+        return cuda_fail(cudaGetLastError(), "cudaMalloc");
+    cudaStream_t st = nullptr;
+    CK(cudaMemcpyAsync(sig.p, h_sig, in_b, cudaMemcpyHostToDevice, st));
+    int rc = b200aa_clip_stats(sig.p, dtype, n_clips, n_samples, n_samples, nullptr, (b200aa_clip_norm *)nm.p, st);
+    if (rc) return rc;
+    rc = b200aa_st_features(plan, sig.p, dtype, n_clips, n_samples, n_samples, nullptr, (b200aa_clip_norm *)nm.p, deltas,
+                            (float *)out.p, T, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_out, out.p, out_b, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200AA_OK;
+}
+
+extern "C" int b200aa_spectrogram_host(const b200aa_plan *plan, const void *h_sig, int dtype, int64_t n_samples, float *h_out)
+{
+    if (!plan || !h_sig || !h_out || (dtype != 0 && dtype != 1)) return B200AA_ERR_INVALID;
+    const int64_t R = b200aa_spectrogram_rows(n_samples, plan->window, plan->step);
+    if (R <= 0) return B200AA_ERR_TOO_SHORT;
+    const size_t in_b = size_t(n_samples) * (dtype == 0 ? 2 : 4), out_b = size_t(R) * plan->K * 4;
+    DevBuf sig, nm, out;
+    if (sig.alloc(in_b) || nm.alloc(sizeof(b200aa_clip_norm)) || out.alloc(out_b)) return cuda_fail(cudaGetLastError(), "cudaMalloc");
+    cudaStream_t st = nullptr;
+    CK(cudaMemcpyAsync(sig.p, h_sig, in_b, cudaMemcpyHostToDevice, st));
+    int rc = b200aa_clip_stats(sig.p, dtype, 1, n_samples, n_samples, nullptr, (b200aa_clip_norm *)nm.p, st);
+    if (rc) return rc;
+    rc = b200aa_spectrogram(plan, sig.p, dtype, 1, n_samples, n_samples, (b200aa_clip_norm *)nm.p, (float *)out.p, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_out, out.p, out_b, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200AA_OK;
+}
+
+extern "C" int b200aa_chromagram_host(const b200aa_plan *plan, const void *h_sig, int dtype, int64_t n_samples, float *h_out)
+{
+    if (!plan || !h_sig || !h_out || (dtype != 0 && dtype != 1)) return B200AA_ERR_INVALID;
+    const int64_t R = b200aa_chromagram_rows(n_samples, plan->window, plan->step);
+    if (R <= 0 || n_samples - plan->step - plan->window < 0) return B200AA_ERR_TOO_SHORT;
+    const size_t in_b = size_t(n_samples) * (dtype == 0 ? 2 : 4), out_b = size_t(R) * 12 * 4;
+    DevBuf sig, nm, out;
+    if (sig.alloc(in_b) || nm.alloc(sizeof(b200aa_clip_norm)) || out.alloc(out_b)) return cuda_fail(cudaGetLastError(), "cudaMalloc");
+    cudaStream_t st = nullptr;
+    CK(cudaMemcpyAsync(sig.p, h_sig, in_b, cudaMemcpyHostToDevice, st));
+    int rc = b200aa_clip_stats(sig.p, dtype, 1, n_samples, n_samples, nullptr, (b200aa_clip_norm *)nm.p, st);
+    if (rc) return rc;
+    rc = b200aa_chromagram(plan, sig.p, dtype, 1, n_samples, n_samples, (b200aa_clip_norm *)nm.p, (float *)out.p, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_out, out.p, out_b, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200AA_OK;
+}
+
+extern "C" int b200aa_mid_features_host(const b200aa_plan *plan, const void *h_sig, int dtype, int64_t n_samples,
+                                        int ratio, int step_ratio, float *h_mid, float *h_st)
+{
+    if (!plan || !h_sig || !h_mid || ratio < 1 || step_ratio < 1 || (dtype != 0 && dtype != 1)) return B200AA_ERR_INVALID;
+    const int64_t T = b200aa_host::num_frames(n_samples, plan->window, plan->step);
+    if (T == 0) return B200AA_ERR_TOO_SHORT;
+    const int64_t M = b200aa_mid_windows(T, step_ratio);
+    const size_t in_b = size_t(n_samples) * (dtype == 0 ? 2 : 4), st_b = size_t(68) * T * 4, mid_b = size_t(136) * M * 4;
+    DevBuf sig, nm, stb, mid;
+    if (sig.alloc(in_b) || nm.alloc(sizeof(b200aa_clip_norm)) || stb.alloc(st_b) || mid.alloc(mid_b))
+        return cuda_fail(cudaGetLastError(), "cudaMalloc");
+    cudaStream_t st = nullptr;
+    CK(cudaMemcpyAsync(sig.p, h_sig, in_b, cudaMemcpyHostToDevice, st));
+    int rc = b200aa_clip_stats(sig.p, dtype, 1, n_samples, n_samples, nullptr, (b200aa_clip_norm *)nm.p, st);
+    if (rc) return rc;
+    rc = b200aa_st_features(plan, sig.p, dtype, 1, n_samples, n_samples, nullptr, (b200aa_clip_norm *)nm.p, 1, (float *)stb.p, T, st);
+    if (rc) return rc;
+    rc = b200aa_mid_pool((const float *)stb.p, 1, 68, T, T, ratio, step_ratio, (float *)mid.p, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_mid, mid.p, mid_b, cudaMemcpyDeviceToHost, st));
+    if (h_st) CK(cudaMemcpyAsync(h_st, stb.p, st_b, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B200AA_OK;
+}

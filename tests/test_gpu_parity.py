@@ -1,0 +1,195 @@
+"""GPU parity: the CUDA path (through the C ABI) against reference-generated golden vectors and the oracle."""
+import numpy as np
+import pytest
+
+from oracle import st_oracle as O
+from tests.parity import check_features, check_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def P():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import pyaudioanalysis_b200 as pkg
+    from pyaudioanalysis_b200 import _lib
+    assert _lib.lib().b200aa_device_ok() == 0, "not an sm_100 device"
+    pkg.ShortTermFeatures.PRINT_SPECTROGRAM_SHAPE = False
+    return pkg
+
+
+# ------------------------------------------------------------------ golden vectors (unmodified reference)
+def test_doremi_feature_extraction(P, golden_doremi):
+    g = golden_doremi
+    F, names = P.ShortTermFeatures.feature_extraction(g["x"], int(g["fs"]), 0.050 * 16000, 0.025 * 16000)
+    assert names == list(g["names"])
+    assert F.dtype == np.float64 and F.shape == (68, 319)
+    check_features(F, g["st"], 400, "doremi 50/25")
+
+
+def test_doremi_spectrogram_chromagram(P, golden_doremi):
+    g = golden_doremi
+    sp, t, f = P.ShortTermFeatures.spectrogram(g["x"], 16000, 800, 400)
+    assert sp.shape == (319, 400) and not sp[317:].any()
+    check_close(sp, g["spectrogram"], "doremi spectrogram", atol=1e-7)
+    check_close(np.array(t), g["spec_time"], rtol=1e-12, atol=0); check_close(np.array(f), g["spec_freq"], rtol=1e-12, atol=0)
+    ch, t, n = P.ShortTermFeatures.chromagram(g["x"], 16000, 800, 400)
+    assert ch.shape == (318, 12) and n == list(g["chroma_names"])
+    check_close(ch, g["chromagram"], "doremi chromagram (last row from a clipped frame)", atol=1e-6)
+    check_close(np.array(t), g["chroma_time"], rtol=1e-12, atol=0)
+
+
+def test_doremi_mid(P, golden_doremi):
+    g = golden_doremi
+    mid, st, names = P.MidTermFeatures.mid_feature_extraction(g["x"], 16000, 16000, 16000, 800, 400)
+    assert names == list(g["mid_names"]) and mid.shape == (136, 8) and st.shape == (68, 319)
+    check_close(mid, g["mid"], "doremi mid-term")
+    check_features(st, g["st"], 400, "doremi st via mid")
+
+
+def test_reference_pytest_inputs(P, golden_pytests):
+    """The reference's own two tests (pytests/test_feature_extraction.py) + values."""
+    g = golden_pytests
+    F, names = P.ShortTermFeatures.feature_extraction(g["x1"], int(g["fs1"]), 0.050 * 16000, 0.050 * 16000)
+    assert F.shape[1] == 20 and F.shape[0] == len(names)
+    check_features(F, g["st1"], 400, "1_sec_wav")
+    mt, st, mt_names = P.MidTermFeatures.mid_feature_extraction(g["x5"], 16000, 1 * 16000, 1 * 16000, 0.05 * 16000, 0.05 * 16000)
+    assert mt.shape[1] == 5 and mt.shape[0] == len(mt_names) == 136
+    check_close(mt, g["mid5"], "5_sec_wav mid")
+    check_features(st, g["st5"], 400, "5_sec_wav st")
+
+
+def test_synthetic_goldens(P, golden_synth):
+    g = golden_synth
+    for idx in (0, 1, 2):
+        F, _ = P.ShortTermFeatures.feature_extraction(O.synth_clip(idx, 32000, 16000), 16000, 800, 400)
+        check_features(F, g[f"st16_{idx}"], 400, f"synthetic 16k clip {idx}")
+    c44 = O.synth_clip(7, 44100, 44100)
+    F, _ = P.ShortTermFeatures.feature_extraction(c44, 44100, 882, 441)
+    check_features(F, g["st44"], 441, "synthetic 44.1k 20/10 ms")
+    check_close(P.ShortTermFeatures.spectrogram(c44, 44100, 882, 441)[0], g["sp44"], "spectrogram 44.1k", atol=1e-7)
+    check_close(P.ShortTermFeatures.chromagram(c44, 44100, 882, 441)[0], g["ch44"], "chromagram 44.1k", atol=1e-6)
+
+
+def test_float_input_odd_window(P, golden_synth):
+    cf = O.synth_clip(11, 20000, 22050).astype(np.float64) * 0.37 + 11.5
+    F, names = P.ShortTermFeatures.feature_extraction(cf, 22050, 551, 200, deltas=False)
+    assert len(names) == 34
+    check_features(F, golden_synth["st_float_551"], 275, "float64 input, window 551, step 200, no deltas")
+
+
+def test_one_second_windows(P, golden_synth):
+    """music_thumbnailing calls the path with 1 s windows (audioSegmentation.py:1137-1139)."""
+    F, _ = P.ShortTermFeatures.feature_extraction(O.synth_clip(13, 80000, 16000), 16000, 16000, 16000)
+    check_features(F, golden_synth["st_win16000"], 8000, "window = step = 16000")
+
+
+def test_mid_awkward_ratio(P, golden_synth):
+    mid, st, _ = P.MidTermFeatures.mid_feature_extraction(O.synth_clip(3, 50000, 16000), 16000, 16000, 8000, 800, 400)
+    check_close(mid, golden_synth["mid_16000_8000"], "mid 1.0/0.5 s")
+
+
+def test_edges(P, golden_edges):
+    g = golden_edges
+    S = P.ShortTermFeatures
+    Fz, _ = S.feature_extraction(np.zeros(4000, dtype=np.int16), 16000, 800, 400)
+    check_features(Fz, g["zeros"], 400, "all-zero clip")
+    assert abs(Fz[8, 0] - (-99.00180475419432)) < 1e-3
+    Fk, _ = S.feature_extraction(np.full(4000, 1234, dtype=np.int16), 16000, 800, 400)
+    check_features(Fk[:8], g["const"][:8], 400, "constant clip (time/spectral rows)")
+    for n in (800, 1199, 1200):
+        F, _ = S.feature_extraction(O.synth_clip(5, n, 16000), 16000, 800, 400)
+        check_features(F, g[f"n{n}"], 400, f"N={n}")
+    with pytest.raises(ValueError, match="need at least one array"):
+        S.feature_extraction(O.synth_clip(5, 799, 16000), 16000, 800, 400)
+    with pytest.raises(ValueError):
+        S.feature_extraction(O.synth_clip(5, 4000, 8000), 8000, 160, 80)     # chroma else-branch of the reference
+    Fs, _ = S.feature_extraction(g["silence_x"], 16000, 800, 400)
+    check_features(Fs, g["silence"], 400, "digital silence inside a clip with DC offset")
+    cc = O.synth_clip(22, 16300, 16000)
+    check_close(S.chromagram(cc, 16000, 800, 400)[0], g["chroma_clipped"], "chromagram, clipped last frame", atol=1e-6)
+    check_close(S.spectrogram(cc, 16000, 800, 400)[0], g["spec_16300"], "spectrogram N=16300", atol=1e-7)
+
+
+# ------------------------------------------------------------------ oracle on seeded inputs
+@pytest.mark.parametrize("fs,w,s,n", [(16000, 800, 400, 48000), (16000, 800, 800, 16000), (16000, 640, 160, 20000),
+                                      (44100, 882, 441, 30000), (8000, 400, 200, 12000), (22050, 1102, 551, 30000),
+                                      (48000, 2400, 1200, 60000), (16000, 1024, 512, 20000), (16000, 883, 300, 9000)])
+def test_oracle_configs(P, fs, w, s, n):
+    x = O.synth_clip(100 + w, n, fs)
+    ref, names = O.feature_extraction(x, fs, w, s)
+    F, names2 = P.ShortTermFeatures.feature_extraction(x, fs, w, s)
+    assert names == names2
+    check_features(F, ref, w // 2, f"fs={fs} w={w} s={s}")
+
+
+def test_batch_and_ragged(P):
+    import torch
+    clips = np.stack([O.synth_clip(i, 32000, 16000) for i in range(5)])
+    d = torch.from_numpy(clips).cuda()
+    out = P.feature_extraction_batch(d, 16000, 800, 400)
+    assert out.shape == (5, 68, 79) and out.dtype == torch.float32 and out.is_cuda
+    for i in range(5):
+        check_features(out[i].cpu().numpy(), O.feature_extraction(clips[i], 16000, 800, 400)[0], 400, f"batch clip {i}")
+    lens = torch.tensor([32000, 800, 12345, 31999, 20000], dtype=torch.int64, device="cuda")
+    out = P.feature_extraction_batch(d, 16000, 800, 400, lengths=lens)
+    for i, L in enumerate(lens.tolist()):
+        ref = O.feature_extraction(clips[i][:L], 16000, 800, 400)[0]
+        got = out[i].cpu().numpy()
+        check_features(got[:, :ref.shape[1]], ref, 400, f"ragged clip {i}")
+        assert not got[:, ref.shape[1]:].any()
+    f32 = torch.from_numpy(clips.astype(np.float32) * 3.0).cuda()
+    outf = P.feature_extraction_batch(f32, 16000, 800, 400, deltas=False)
+    for i in range(5):
+        check_features(outf[i].cpu().numpy(), O.feature_extraction(clips[i], 16000, 800, 400, deltas=False)[0], 400, f"f32 clip {i}")
+
+
+def test_mid_pool_kernel(P):
+    import torch
+    from pyaudioanalysis_b200.batch import mid_pool_batch
+    st = torch.randn(3, 68, 399, device="cuda")
+    mid = mid_pool_batch(st, 39, 40).cpu().numpy()
+    ref = np.stack([O.mid_pool(st[i].cpu().numpy().astype(np.float64), 39, 40) for i in range(3)])
+    check_close(mid, ref, "mid_pool", rtol=1e-5, atol=1e-6)
+
+
+def test_kernel_kinds_agree(P):
+    """Where a specialised kernel exists it must agree with the generic one (and both with the oracle)."""
+    import torch
+    from pyaudioanalysis_b200._lib import Plan
+    for fs, w, s in [(16000, 800, 400), (44100, 882, 441), (16000, 800, 800), (16000, 800, 200)]:
+        clips = np.stack([O.synth_clip(40 + i, 24000, fs) for i in range(3)])
+        d = torch.from_numpy(clips).cuda()
+        pf, pg = Plan(fs, w, s), Plan(fs, w, s)
+        pg.force_generic(True)
+        a = P.feature_extraction_batch(d, fs, w, s, plan=pf).cpu().numpy()
+        b = P.feature_extraction_batch(d, fs, w, s, plan=pg).cpu().numpy()
+        assert pg.kernel_kind() == 0
+        for i in range(3):
+            ref = O.feature_extraction(clips[i], fs, w, s)[0]
+            check_features(a[i], ref, w // 2, f"default kernel (kind {pf.kernel_kind()}) fs={fs} w={w} s={s}")
+            check_features(b[i], ref, w // 2, f"generic kernel fs={fs} w={w} s={s}")
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE configs[1])
+def test_full_size_properties(P):
+    """1000 x 10 s @16 kHz: no oracle at this size -- use properties that do not depend on it."""
+    import torch
+    torch.manual_seed(0)
+    B, N = 1000, 160000
+    base = (3000.0 * torch.randn(B, N, device="cuda")).round().clamp(-16000, 16000).to(torch.int16)
+    base[1] = base[0]                      # identical clips -> identical features
+    base[3] = (base[2].to(torch.int32) * 2).to(torch.int16)   # gain 2 (no clipping): normalisation removes it
+    out = P.feature_extraction_batch(base, 16000, 800, 400)
+    assert out.shape == (B, 68, 399) and torch.isfinite(out).all()
+    assert torch.equal(out[0], out[1])
+    torch.testing.assert_close(out[3], out[2], rtol=1e-4, atol=2e-5)
+    # deltas are the first difference of the base rows, zero in column 0
+    torch.testing.assert_close(out[:, 34:, 1:], out[:, :34, 1:] - out[:, :34, :-1], rtol=0, atol=0)
+    assert not out[:, 34:, 0].any()
+    # spot-check five clips against the oracle
+    for i in (0, 2, 499, 998, 999):
+        check_features(out[i].cpu().numpy(), O.feature_extraction(base[i].cpu().numpy(), 16000, 800, 400)[0], 400, f"cfg2 clip {i}")
+    # chroma rows sum to <= 1 and are non-negative; energy equals mean square of normalised samples
+    assert (out[:, 21:33] >= 0).all()
