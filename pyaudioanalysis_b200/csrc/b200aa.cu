@@ -284,7 +284,7 @@ static int feature_tables_status(const b200aa_plan *pl)
 
 // ------------------------------------------------------------------------------------------------
 // kernel 0: clip statistics  (signal / 2**15 + dc_normalize, ShortTermFeatures.py:567-570, :14-19)
-// accumulators live in the output records: rsv[0..1] = sum (int64 / double), lo/hi = min/max keys
+// accumulators live in the output records: rsv[1..2] (8-byte aligned) = sum (int64 / double), lo/hi = min/max keys
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int float_key(float f)
 {
@@ -297,7 +297,7 @@ __global__ void stats_init_kernel(b200aa_clip_norm *nm, int64_t n)
 {
     int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     if (i >= n) return;
-    unsigned long long *acc = reinterpret_cast<unsigned long long *>(&nm[i].rsv[0]);
+    unsigned long long *acc = reinterpret_cast<unsigned long long *>(&nm[i].rsv[1]);
     *acc = 0ull;
     reinterpret_cast<int *>(&nm[i].lo)[0] = 0x7fffffff;              // running min key
     reinterpret_cast<int *>(&nm[i].hi)[0] = int(0x80000000u);        // running max key
@@ -372,9 +372,9 @@ __global__ void __launch_bounds__(256) stats_accum_kernel(const void *sig, int64
     if (threadIdx.x == 0 && s1 > s0) {
         for (int w = 1; w < 8; ++w) { isum += s_i[w]; dsum += s_d[w]; kmin = min(kmin, s_mn[w]); kmax = max(kmax, s_mx[w]); }
         if (DTYPE == B200AA_DTYPE_I16)
-            atomicAdd(reinterpret_cast<unsigned long long *>(&nm[b].rsv[0]), (unsigned long long)isum);
+            atomicAdd(reinterpret_cast<unsigned long long *>(&nm[b].rsv[1]), (unsigned long long)isum);
         else
-            atomicAdd(reinterpret_cast<double *>(&nm[b].rsv[0]), dsum);
+            atomicAdd(reinterpret_cast<double *>(&nm[b].rsv[1]), dsum);
         atomicMin(reinterpret_cast<int *>(&nm[b].lo), kmin);
         atomicMax(reinterpret_cast<int *>(&nm[b].hi), kmax);
     }
@@ -389,12 +389,12 @@ __global__ void stats_finish_kernel(b200aa_clip_norm *nm, int64_t n, int64_t n_s
     b200aa_clip_norm r = nm[i];
     double mean, mn, mx;
     if (DTYPE == B200AA_DTYPE_I16) {
-        const long long s = *reinterpret_cast<const long long *>(&r.rsv[0]);
+        const long long s = *reinterpret_cast<const long long *>(&nm[i].rsv[1]);
         mean = L > 0 ? double(s) / double(L) : 0.0;
         mn = double(*reinterpret_cast<const int *>(&r.lo));
         mx = double(*reinterpret_cast<const int *>(&r.hi));
     } else {
-        const double s = *reinterpret_cast<const double *>(&r.rsv[0]);
+        const double s = *reinterpret_cast<const double *>(&nm[i].rsv[1]);
         mean = L > 0 ? s / double(L) : 0.0;
         mn = double(key_float(*reinterpret_cast<const int *>(&r.lo)));
         mx = double(key_float(*reinterpret_cast<const int *>(&r.hi)));

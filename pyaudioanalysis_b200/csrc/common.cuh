@@ -200,20 +200,27 @@ __device__ __forceinline__ void spectral_features(const float *X, const float *X
         const float s = e / (sxx + B200AA_EPS);
         ent -= s * log2f(s + B200AA_EPS);
     }
-    // mfcc [:236-254]: 40 sparse triangular filters, log10, 13 DCT rows
+    // mfcc [:236-254]: 40 sparse triangular filters, log10, 13 DCT rows.
+    // DCT rows 1..12 are orthogonal to constants, so they are applied to (m - mean(m)): identical
+    // in exact arithmetic, and it removes the float32 cancellation error when the log-mel
+    // spectrum is nearly flat (digital silence: every m equals log10(eps) = -15.65).
+    float msum = 0.f;
     for (int i = lane; i < B200AA_N_MEL; i += 32) {
         const int s0 = tb.mel_start[i], cnt = tb.mel_count[i], off = tb.mel_off[i];
         float acc = 0.f;
         for (int j = 0; j < cnt; ++j) acc = fmaf(X[s0 + j], tb.mel_w[off + j], acc);
-        mscratch[i] = log10f(acc + B200AA_EPS);
+        const float m = log10f(acc + B200AA_EPS);
+        mscratch[i] = m;
+        msum += m;
     }
+    const float mbar = warp_sum(msum) * (1.f / float(B200AA_N_MEL));
     __syncwarp();
     if (lane < B200AA_N_MFCC) {
         float acc = 0.f;
         const float *row = tb.dct + lane * 41;
 #pragma unroll 8
-        for (int n = 0; n < B200AA_N_MEL; ++n) acc = fmaf(row[n], mscratch[n], acc);
-        fv[8 + lane] = acc;
+        for (int n = 0; n < B200AA_N_MEL; ++n) acc = fmaf(row[n], mscratch[n] - mbar, acc);
+        fv[8 + lane] = lane == 0 ? 6.324555320336759f * mbar : acc;     // row 0: sqrt(1/40) * sum(m)
     }
     // chroma [:277-321] + population std of the 12 values [:667]
     const float ch = chroma_lane(X, sxx, tb, lane);

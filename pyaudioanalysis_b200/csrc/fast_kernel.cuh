@@ -1,25 +1,431 @@
-// Register-tiled short-term kernels specialised per window length.
+// Register-tiled short-term kernel for even windows N = 2*R*R (R = 20 -> 800 samples = 50 ms @ 16 kHz,
+// R = 21 -> 882 samples = 20 ms @ 44.1 kHz).
+//
+// The real frame is packed into R*R complex points z[n] = x[2n] + i x[2n+1] and transformed as an
+// R x R two-pass FFT: every pass is one R-point FFT per thread held entirely in registers
+// (prime-factor 4x5 / 3x7 butterflies, all twiddles compile-time constants), with one padded
+// shared-memory transpose between the passes.  R threads own a frame; 8 frames per CTA step.
+// Post-processing computes X[k] and X[Nc-k] from one (Z[k], Z[Nc-k]) pair, so only half of the
+// second-pass outputs travel through shared memory.
 #pragma once
 #include <vector>
 #include "common.cuh"
 
 namespace b200aa {
 
+// ----------------------------------------------------------------------------------------------
+// compile-time trigonometry (exact argument reduction in turns, Taylor series in double)
+// ----------------------------------------------------------------------------------------------
+constexpr double kCxPi = 3.14159265358979323846264338327950288;
+
+__host__ __device__ constexpr double cx_sin_small(double x)   // |x| <= pi/2
+{
+    double x2 = x * x, term = x, sum = x;
+    for (int i = 1; i < 16; ++i) { term *= -x2 / double((2 * i) * (2 * i + 1)); sum += term; }
+    return sum;
+}
+__host__ __device__ constexpr double cx_cos_small(double x)
+{
+    double x2 = x * x, term = 1.0, sum = 1.0;
+    for (int i = 1; i < 16; ++i) { term *= -x2 / double((2 * i - 1) * (2 * i)); sum += term; }
+    return sum;
+}
+// cos / sin of 2*pi*p/q
+__host__ __device__ constexpr double cx_cos_turn(long p, long q)
+{
+    p %= q; if (p < 0) p += q;
+    if (2 * p > q) p = q - p;                 // cos(2 pi (1 - r)) = cos(2 pi r)
+    if (4 * p > q) return -cx_cos_small(2.0 * kCxPi * double(q - 2 * p) / double(2 * q));   // cos(pi - y) = -cos y
+    return cx_cos_small(2.0 * kCxPi * double(p) / double(q));
+}
+__host__ __device__ constexpr double cx_sin_turn(long p, long q)
+{
+    p %= q; if (p < 0) p += q;
+    double sign = 1.0;
+    if (2 * p > q) { p = q - p; sign = -1.0; }            // sin(2 pi (1 - r)) = -sin(2 pi r)
+    if (4 * p > q) return sign * cx_sin_small(2.0 * kCxPi * double(q - 2 * p) / double(2 * q));   // sin(pi - y) = sin y
+    return sign * cx_sin_small(2.0 * kCxPi * double(p) / double(q));
+}
+
+template <int P>
+struct Trig { float c[P], s[P]; };
+template <int P>
+__host__ __device__ constexpr Trig<P> make_trig()
+{
+    Trig<P> t{};
+    for (int j = 0; j < P; ++j) { t.c[j] = float(cx_cos_turn(j, P)); t.s[j] = float(cx_sin_turn(j, P)); }
+    return t;
+}
+__host__ __device__ constexpr int cx_modinv(int a, int m)
+{
+    a %= m;
+    for (int x = 1; x < m; ++x) if ((a * x) % m == 1) return x;
+    return 1;
+}
+
+// ----------------------------------------------------------------------------------------------
+// small forward DFTs on register arrays
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+template <int P>
+__device__ __forceinline__ void dft_small(float2 (&x)[P])
+{
+    if constexpr (P == 2) {
+        const float2 a = x[0], b = x[1];
+        x[0] = f2add(a, b); x[1] = f2sub(a, b);
+    } else if constexpr (P == 4) {
+        const float2 a = f2add(x[0], x[2]), b = f2sub(x[0], x[2]), c = f2add(x[1], x[3]), d = f2sub(x[1], x[3]);
+        x[0] = f2add(a, c);
+        x[2] = f2sub(a, c);
+        x[1] = make_float2(b.x + d.y, b.y - d.x);      // b - i d
+        x[3] = make_float2(b.x - d.y, b.y + d.x);      // b + i d
+    } else {
+        // odd prime: y_k = x0 + sum_j [ (x_j + x_{P-j}) cos(2 pi j k / P) - i (x_j - x_{P-j}) sin(2 pi j k / P) ]
+        constexpr Trig<P> T = make_trig<P>();
+        constexpr int H = (P - 1) / 2;
+        float2 sp[H], dm[H], y[P];
+#pragma unroll
+        for (int j = 1; j <= H; ++j) { sp[j - 1] = f2add(x[j], x[P - j]); dm[j - 1] = f2sub(x[j], x[P - j]); }
+        y[0] = x[0];
+#pragma unroll
+        for (int j = 0; j < H; ++j) y[0] = f2add(y[0], sp[j]);
+#pragma unroll
+        for (int k = 1; k <= H; ++k) {
+            float2 re = x[0], im = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 1; j <= H; ++j) {
+                const float c = T.c[(j * k) % P], s = T.s[(j * k) % P];
+                re.x = fmaf(c, sp[j - 1].x, re.x);
+                re.y = fmaf(c, sp[j - 1].y, re.y);
+                im.x = fmaf(s, dm[j - 1].x, im.x);
+                im.y = fmaf(s, dm[j - 1].y, im.y);
+            }
+            y[k] = make_float2(re.x + im.y, re.y - im.x);
+            y[P - k] = make_float2(re.x - im.y, re.y + im.x);
+        }
+#pragma unroll
+        for (int k = 0; k < P; ++k) x[k] = y[k];
+    }
+}
+
+// prime-factor FFT of length RA*RB (coprime), natural order in, natural order out
+template <int RA, int RB>
+__device__ __forceinline__ void fft_pfa(float2 (&v)[RA * RB])
+{
+    constexpr int N = RA * RB;
+    float2 U[N];
+#pragma unroll
+    for (int a = 0; a < RA; ++a) {
+        float2 t[RB];
+#pragma unroll
+        for (int b = 0; b < RB; ++b) t[b] = v[(RB * a + RA * b) % N];
+        dft_small<RB>(t);
+#pragma unroll
+        for (int b = 0; b < RB; ++b) U[a * RB + b] = t[b];
+    }
+    constexpr int ca = RB * cx_modinv(RB, RA), cb = RA * cx_modinv(RA, RB);
+#pragma unroll
+    for (int kb = 0; kb < RB; ++kb) {
+        float2 t[RA];
+#pragma unroll
+        for (int a = 0; a < RA; ++a) t[a] = U[a * RB + kb];
+        dft_small<RA>(t);
+#pragma unroll
+        for (int ka = 0; ka < RA; ++ka) v[(ka * ca + kb * cb) % N] = t[ka];
+    }
+}
+
+template <int R> struct RFactors;
+template <> struct RFactors<20> { static constexpr int A = 4, B = 5; };
+template <> struct RFactors<21> { static constexpr int A = 3, B = 7; };
+
+template <int R>
+__device__ __forceinline__ void fft_r(float2 (&v)[R]) { fft_pfa<RFactors<R>::A, RFactors<R>::B>(v); }
+
+// ----------------------------------------------------------------------------------------------
+// kernel
+// ----------------------------------------------------------------------------------------------
 struct FastTables {
-    void release() {}
+    float2 *d_tw = nullptr;      // [R][R]   W_Nc^(k1*n2) stored [k1][n2]
+    float2 *d_twp = nullptr;     // [Nc/2+1] W_N^k
+    int R = 0;
+    void release()
+    {
+        if (d_tw) cudaFree(d_tw);
+        if (d_twp) cudaFree(d_twp);
+        d_tw = d_twp = nullptr;
+    }
 };
+
+constexpr int kFastG = 8;   // frames per CTA step
+
+template <int R>
+struct FastShape {
+    static constexpr int Nc = R * R, N = 2 * Nc, K = Nc, Kp = (K + 3) & ~3;
+    static constexpr int ES = R | 1;             // padded row stride of the transpose buffer (float2)
+    static constexpr int H = R / 2;              // second-pass outputs k2 >= H are published for the partners
+    static constexpr int ZS = Nc - R * H;        // published values per frame
+    static constexpr int FftThreads = kFastG * R;
+};
+
+template <int R>
+inline size_t fast_smem_bytes(int step, int blob_words)
+{
+    using S = FastShape<R>;
+    size_t b = 0;
+    b += size_t((kFastG - 1) * step + S::N + 4) * sizeof(float);          // sample span
+    b += size_t(kFastG) * R * S::ES * sizeof(float2);                     // transpose buffer (rows 1..8 of |X| alias it)
+    b += size_t(kFastG) * S::ZS * sizeof(float2);                         // published second-pass outputs
+    b += size_t(S::Kp) * sizeof(float);                                   // |X| of the previous frame
+    b += size_t(kFastG + 1) * kFvStride * sizeof(float);
+    b += size_t(kWarps) * B200AA_N_MEL * sizeof(float);
+    b += size_t(kFastG + 1) * sizeof(float) + 16;
+    b += size_t(R) * R * sizeof(float2) + size_t(S::Nc / 2 + 1) * sizeof(float2);
+    b += size_t(blob_words) * sizeof(int);
+    return (b + 15) & ~size_t(15);
+}
+
+template <int R, bool STEP_EVEN>
+__global__ void __launch_bounds__(kThreads, 2) st_fast_kernel(const StParams p, const float2 *__restrict__ g_tw,
+                                                                const float2 *__restrict__ g_twp)
+{
+    using S = FastShape<R>;
+    constexpr int Nc = S::Nc, N = S::N, K = S::K, Kp = S::Kp, ES = S::ES, H = S::H, ZS = S::ZS, G = kFastG;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int step = p.step;
+    const int span_max = (G - 1) * step + N;
+    float2 *E = reinterpret_cast<float2 *>(smem_raw);                       // [G][R][ES]
+    float2 *Zs = E + size_t(G) * R * ES;                                      // [G][ZS]
+    float2 *s_tw = Zs + size_t(G) * ZS;                                       // [R][R]
+    float2 *s_twp = s_tw + R * R;                                             // [Nc/2+1]
+    float *sS = reinterpret_cast<float *>(s_twp + (Nc / 2 + 1));             // sample span (8-byte aligned)
+    float *Xprev = sS + ((span_max + 4) & ~3);                               // [Kp]
+    float *fvrows = Xprev + Kp;                                              // [(G+1)][36]
+    float *mscr = fvrows + (G + 1) * kFvStride;
+    float *rowsum = mscr + kWarps * B200AA_N_MEL;
+    int *blob_s = reinterpret_cast<int *>(rowsum + (G + 1) + 3);
+    float *Xrows = reinterpret_cast<float *>(E);                             // rows f -> Xrows + f*Kp (aliases E)
+    static_assert(size_t(G) * Kp * sizeof(float) <= size_t(G) * R * ES * sizeof(float2), "alias");
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < p.bl.words; i += kThreads) blob_s[i] = p.blob[i];
+    for (int i = tid; i < R * R; i += kThreads) s_tw[i] = g_tw[i];
+    for (int i = tid; i < Nc / 2 + 1; i += kThreads) s_twp[i] = g_twp[i];
+    __syncthreads();
+    const SmallTables tb = bind_tables(blob_s, p.bl);
+    const bool fft_thread = tid < S::FftThreads;
+    const int ff = tid / R, fj = tid - ff * R;          // frame slot / index within the frame's R threads
+
+    for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int64_t b = item / p.segs_per_clip, seg = item % p.segs_per_clip;
+        const int64_t len = p.len ? p.len[b] : p.n_samples;
+        const int64_t T = len < N ? 0 : (len - N) / step + 1;
+        const int64_t t0 = seg * p.seg_len;
+        if (t0 >= T) continue;
+        const int64_t t1 = (t0 + p.seg_len) < T ? (t0 + p.seg_len) : T;
+        const b200aa_clip_norm nm = p.norm[b];
+        const char *clip = reinterpret_cast<const char *>(p.sig) +
+                           size_t(b) * p.clip_stride * (p.dtype == B200AA_DTYPE_I16 ? 2 : 4);
+        const SampleReader rd{clip, p.dtype, nm.m};
+        const int halo = int(t0 < 2 ? t0 : 2);
+
+        for (int64_t g0 = t0 - halo; g0 < t1; g0 += G) {
+            const int ng = int((t1 - g0) < G ? (t1 - g0) : G);
+            // ---- stage the sample span of this step as float (x - m)
+            const int span = (ng - 1) * step + N;
+            const int64_t sbase = g0 * step;
+            for (int i = tid; i < span; i += kThreads) sS[i] = rd(sbase + i);
+            __syncthreads();
+
+            // ---- pass 1: thread (frame ff, column n2 = fj): FFT over n1 of z[R*n1 + n2], twiddle, transpose
+            if (fft_thread && ff < ng) {
+                const float *fr = sS + ff * step;
+                const float d0 = fr[0];
+                float2 v[R];
+#pragma unroll
+                for (int n1 = 0; n1 < R; ++n1) {
+                    float2 z;
+                    if (STEP_EVEN) z = *reinterpret_cast<const float2 *>(fr + 2 * (R * n1 + fj));
+                    else { z.x = fr[2 * (R * n1 + fj)]; z.y = fr[2 * (R * n1 + fj) + 1]; }
+                    v[n1] = make_float2(z.x - d0, z.y - d0);
+                }
+                fft_r<R>(v);
+                float2 *Ef = E + size_t(ff) * R * ES;
+#pragma unroll
+                for (int k1 = 0; k1 < R; ++k1) {
+                    const float2 w = k1 == 0 ? make_float2(1.f, 0.f) : s_tw[k1 * R + fj];
+                    Ef[k1 * ES + fj] = k1 == 0 ? v[0] : cmul(v[k1], w);
+                }
+            }
+            __syncthreads();
+            // ---- pass 2: thread (frame ff, row k1 = fj): FFT over n2 -> Z[k1 + R*k2]
+            float2 v[R];
+            if (fft_thread && ff < ng) {
+                const float2 *Ef = E + size_t(ff) * R * ES + fj * ES;
+#pragma unroll
+                for (int n2 = 0; n2 < R; ++n2) v[n2] = Ef[n2];
+                fft_r<R>(v);
+                float2 *Zf = Zs + size_t(ff) * ZS;
+#pragma unroll
+                for (int k2 = H; k2 < R; ++k2) Zf[fj + R * (k2 - H)] = v[k2];
+            }
+            __syncthreads();    // all E reads done (|X| rows alias E) and partner values visible
+            // ---- post-process: X[k] = ev + W_N^k od, X[Nc-k] = conj(ev - W_N^k od) from (Z[k], Z[Nc-k])
+            if (fft_thread && ff < ng) {
+                const float2 *Zf = Zs + size_t(ff) * ZS;
+                float *Xf = Xrows + size_t(ff) * Kp;
+                const float sc = nm.a / float(2 * K);
+                auto pair = [&](int k, float2 zk, bool do_mirror) {
+                    const float2 zp = Zf[(Nc - k) - R * H];
+                    const float2 ev = make_float2(zk.x + zp.x, zk.y - zp.y);
+                    const float2 od = make_float2(zk.y + zp.y, zp.x - zk.x);
+                    const float2 t = cmul(od, s_twp[k]);
+                    const float ar = (ev.x + t.x) * sc, ai = (ev.y + t.y) * sc;
+                    const float br = (ev.x - t.x) * sc, bi = (ev.y - t.y) * sc;
+                    Xf[k] = sqrtf(fmaf(ar, ar, ai * ai));
+                    if (do_mirror) Xf[Nc - k] = sqrtf(fmaf(br, br, bi * bi));
+                };
+#pragma unroll
+                for (int k2 = 0; k2 < H; ++k2) {
+                    const int k = fj + R * k2;
+                    if (k2 == 0 && fj == 0) {
+                        // DC: a * sum(d - d0) + N * (a*d0 + bp)
+                        const float d0 = sS[ff * step];
+                        Xf[0] = fabsf(fmaf(nm.a, v[0].x + v[0].y, float(N) * fmaf(nm.a, d0, nm.bp))) / float(K);
+                    } else {
+                        pair(k, v[k2], true);
+                    }
+                }
+                {   // middle index k2 = H: only the lower partner of each pair computes it
+                    const int k = fj + R * H;
+                    if (2 * k < Nc) pair(k, v[H], true);
+                    else if (2 * k == Nc) {          // self-paired bin Nc/2 (R even, thread 0): |X| = |Z|
+                        const float ar = v[H].x * 2.f * sc, ai = v[H].y * 2.f * sc;
+                        Xf[k] = sqrtf(fmaf(ar, ar, ai * ai));
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---- features: one warp per frame
+            for (int f = warp; f < ng; f += kWarps) {
+                const int64_t fr = g0 + f;
+                const float *X = Xrows + size_t(f) * Kp;
+                const bool has_prev = (fr > 0) && !(f == 0 && g0 == t0 - halo);
+                float sxp;
+                const float *Xp;
+                float *fv = fvrows + size_t(f + 1) * kFvStride;
+                const float *frs = sS + f * step;
+                time_features([&](int n) { return frs[n]; }, N, nm, fv, lane);
+                if (has_prev && f > 0) {
+                    Xp = Xrows + size_t(f - 1) * Kp;
+                    float s = 0.f;
+                    for (int k = lane; k < K; k += 32) s += Xp[k];
+                    sxp = warp_sum(s);
+                } else if (has_prev) {
+                    Xp = Xprev;
+                    sxp = rowsum[0];
+                } else {
+                    Xp = X;
+                    float s = 0.f;
+                    for (int k = lane; k < K; k += 32) s += X[k];
+                    sxp = warp_sum(s);
+                }
+                spectral_features(X, Xp, sxp, K, tb, mscr + warp * B200AA_N_MEL, fv, lane, rowsum + f + 1);
+            }
+            __syncthreads();
+            // ---- store [n_out x ng] tile: consecutive threads -> consecutive frames
+            for (int e = tid; e < p.n_out * ng; e += kThreads) {
+                const int f = e / ng, c = e - f * ng;
+                const int64_t fr = g0 + c;
+                if (fr < t0) continue;
+                float val;
+                if (f < B200AA_N_BASE) val = fvrows[size_t(c + 1) * kFvStride + f];
+                else {
+                    const int fb = f - B200AA_N_BASE;
+                    val = fr == 0 ? 0.f : fvrows[size_t(c + 1) * kFvStride + fb] - fvrows[size_t(c) * kFvStride + fb];
+                }
+                p.out[(size_t(b) * p.n_out + f) * p.t_stride + fr] = val;
+            }
+            // ---- carry the last frame of the step
+            for (int k = tid; k < K; k += kThreads) Xprev[k] = Xrows[size_t(ng - 1) * Kp + k];
+            __syncthreads();
+            if (tid < kFvStride) fvrows[tid] = fvrows[size_t(ng) * kFvStride + tid];
+            if (tid == 0) rowsum[0] = rowsum[ng];
+            __syncthreads();
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+inline int fast_r_for_window(int window)
+{
+    if (window == 800) return 20;
+    if (window == 882) return 21;
+    return 0;
+}
 
 inline int fast_plan_init(int fs, int window, int step, const std::vector<int> &blob, const BlobLayout &bl,
                           FastTables *ft, int *kind)
 {
-    (void)fs; (void)window; (void)step; (void)blob; (void)bl; (void)ft;
+    (void)fs; (void)step; (void)blob; (void)bl;
     *kind = 0;
+    const int R = fast_r_for_window(window);
+    if (!R) return B200AA_OK;
+    const int Nc = R * R, N = 2 * Nc;
+    const double pi = 3.14159265358979323846264338327950288;
+    std::vector<float2> tw(size_t(R) * R), twp(Nc / 2 + 1);
+    for (int k1 = 0; k1 < R; ++k1)
+        for (int n2 = 0; n2 < R; ++n2) {
+            const double a = -2.0 * pi * double((k1 * n2) % Nc) / double(Nc);
+            tw[size_t(k1) * R + n2] = make_float2(float(std::cos(a)), float(std::sin(a)));
+        }
+    for (int k = 0; k <= Nc / 2; ++k) {
+        const double a = -2.0 * pi * double(k) / double(N);
+        twp[k] = make_float2(float(std::cos(a)), float(std::sin(a)));
+    }
+    if (cudaMalloc(&ft->d_tw, tw.size() * sizeof(float2)) != cudaSuccess) return B200AA_ERR_CUDA;
+    if (cudaMalloc(&ft->d_twp, twp.size() * sizeof(float2)) != cudaSuccess) return B200AA_ERR_CUDA;
+    if (cudaMemcpy(ft->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) return B200AA_ERR_CUDA;
+    if (cudaMemcpy(ft->d_twp, twp.data(), twp.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) return B200AA_ERR_CUDA;
+    ft->R = R;
+    *kind = R;
     return B200AA_OK;
+}
+
+template <int R, bool EVEN>
+inline int fast_launch_t(const FastTables &ft, StParams p, int sm_count, int64_t T, cudaStream_t st)
+{
+    const size_t smem = fast_smem_bytes<R>(p.step, p.bl.words);
+    if (smem > 110u * 1024u) return B200AA_ERR_UNSUPPORTED;      // very large hop: leave it to the generic kernel
+    auto kern = st_fast_kernel<R, EVEN>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200AA_ERR_CUDA;
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem) != cudaSuccess) return B200AA_ERR_CUDA;
+    occ = occ < 1 ? 1 : occ;
+    const int64_t slots = int64_t(sm_count) * occ;
+    int64_t per_clip = (slots * 12 + p.n_clips - 1) / p.n_clips;
+    if (per_clip < 1) per_clip = 1;
+    int64_t seg = (T + per_clip - 1) / per_clip;
+    if (seg < kFastG * 6 - 2) seg = kFastG * 6 - 2;
+    if (seg > T) seg = T;
+    p.seg_len = seg;
+    p.segs_per_clip = (T + seg - 1) / seg;
+    p.n_items = p.segs_per_clip * p.n_clips;
+    const int64_t grid = p.n_items < slots ? p.n_items : slots;
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(p, ft.d_tw, ft.d_twp);
+    return cudaGetLastError() == cudaSuccess ? B200AA_OK : B200AA_ERR_CUDA;
 }
 
 inline int fast_launch_features(int kind, const FastTables &ft, const StParams &p, int sm_count, int64_t T, cudaStream_t st)
 {
-    (void)kind; (void)ft; (void)p; (void)sm_count; (void)T; (void)st;
+    const bool even = (p.step % 2) == 0;
+    if (kind == 20) return even ? fast_launch_t<20, true>(ft, p, sm_count, T, st) : fast_launch_t<20, false>(ft, p, sm_count, T, st);
+    if (kind == 21) return even ? fast_launch_t<21, true>(ft, p, sm_count, T, st) : fast_launch_t<21, false>(ft, p, sm_count, T, st);
     return B200AA_ERR_UNSUPPORTED;
 }
 

@@ -106,7 +106,14 @@ def test_edges(P, golden_edges):
     with pytest.raises(ValueError):
         S.feature_extraction(O.synth_clip(5, 4000, 8000), 8000, 160, 80)     # chroma else-branch of the reference
     Fs, _ = S.feature_extraction(g["silence_x"], 16000, 800, 400)
-    check_features(Fs, g["silence"], 400, "digital silence inside a clip with DC offset")
+    # Frames 8..15 are digital silence: the reference's non-DC bins there are float64 round-off
+    # (~1e-19) passed through log10(. + eps), which makes its mfcc_2..13 = 3.1e-5 -- noise that even
+    # the float64 oracle does not reproduce (it differs by 3.6e-5, tests/test_oracle_golden.py).  The
+    # GPU transforms (x - x[0]) and gets exact zeros there.  Those frames (and the deltas that touch
+    # them) are held to atol 1e-4 instead of 1e-5; everything else to the standard tolerance.
+    noisy = np.zeros(Fs.shape[1], bool); noisy[8:17] = True
+    check_features(Fs[:, ~noisy], g["silence"][:, ~noisy], 400, "digital silence inside a clip with DC offset")
+    check_close(Fs[:, noisy], g["silence"][:, noisy], "digitally silent frames", rtol=1e-4, atol=1e-4)
     cc = O.synth_clip(22, 16300, 16000)
     check_close(S.chromagram(cc, 16000, 800, 400)[0], g["chroma_clipped"], "chromagram, clipped last frame", atol=1e-6)
     check_close(S.spectrogram(cc, 16000, 800, 400)[0], g["spec_16300"], "spectrogram N=16300", atol=1e-7)
