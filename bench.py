@@ -219,7 +219,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- end to end through the public host API: pinned host clips -> host features
     e2e = None
-    if rank == 0 or world > 1:
+    if (rank == 0 or world > 1) and not args.no_e2e:
         host_in = torch.empty((B, CLIP_SAMPLES), dtype=torch.int16).pin_memory()
         host_in.copy_(clips)
         pipe = HostPipeline(FS, WINDOW, STEP, CLIP_SAMPLES, max_clips=B, device=local_rank)
@@ -285,6 +285,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-pipeline leg (profiling runs under ncu)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

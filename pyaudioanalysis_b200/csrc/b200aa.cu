@@ -2,6 +2,7 @@
 // Build: see pyaudioanalysis_b200/build.py (nvcc -gencode arch=compute_100a,code=sm_100a).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -231,6 +232,14 @@ static int build_blob(int fs, int K, std::vector<int> &blob, BlobLayout &bl, boo
     bl.chr_off = put_i(c_off);
     bl.chr_bin = put_i(c_bin);
     bl.chr_w = put_f(c_w);
+    {   // pair the longest filter with the shortest, 2nd longest with 2nd shortest, ...
+        std::vector<int> order(40);
+        for (int i = 0; i < 40; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return m_count[a] < m_count[b]; });
+        std::vector<int> pairs;
+        for (int i = 0; i < 20; ++i) { pairs.push_back(order[39 - i]); pairs.push_back(order[i]); }
+        bl.mel_pairs = put_i(pairs);
+    }
     while (blob.size() % 4) blob.push_back(0);
     bl.words = (int)blob.size();
     return (rc_chr != B200AA_OK) ? rc_chr : rc_mel;

@@ -23,6 +23,7 @@ struct BlobLayout {
     int chr_off;     // [13] per pitch class: first entry
     int chr_bin;     // [chr_nnz] source bin
     int chr_w;       // [chr_nnz] weight (float)
+    int mel_pairs;   // [20 x 2] filters paired long-with-short (balanced flat mel phase)
     int words;       // total
 };
 

@@ -13,6 +13,8 @@
 
 namespace b200aa {
 
+constexpr int kFastG = 8;   // frames per CTA step
+
 // ----------------------------------------------------------------------------------------------
 // compile-time trigonometry (exact argument reduction in turns, Taylor series in double)
 // ----------------------------------------------------------------------------------------------
@@ -145,6 +147,266 @@ template <int R>
 __device__ __forceinline__ void fft_r(float2 (&v)[R]) { fft_pfa<RFactors<R>::A, RFactors<R>::B>(v); }
 
 // ----------------------------------------------------------------------------------------------
+// spectral features with a compile-time bin count: every lane keeps its C = odd(ceil(K/32))
+// consecutive bins in registers (odd stride => conflict-free loads) and all dense reductions run
+// on those registers.  Same arithmetic as spectral_features() in common.cuh.
+// ----------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void spectral_features_k(const float *X, const float *Xp, float sxp, const float *chroma_raw,
+                                                    float *fv, int lane, float *sx_out)
+{
+    constexpr int C = ((K + 31) / 32) | 1;
+    constexpr int Lb = K / 10;                     // spectral-entropy block length (:94)
+    const int k0 = lane * C;
+    float x[C];
+#pragma unroll
+    for (int i = 0; i < C; ++i) x[i] = (k0 + i < K) ? X[k0 + i] : 0.f;
+    // ---- sums: sum X, sum (k+1) X, sum X^2 (with the part below / above an entropy-block boundary)
+    // the single multiple of Lb that can fall inside (k0, k0 + C): C < Lb
+    static_assert(C < Lb, "a lane may straddle at most one entropy block boundary");
+    const int bnd = ((k0 + C - 1) / Lb) * Lb;      // first bin of the block that contains the lane's last bin
+    const int split = bnd > k0 ? bnd - k0 : 0;     // bins [0, split) belong to the previous block
+    float sx = 0.f, s1 = 0.f, plo = 0.f, phi = 0.f;
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+        sx += x[i];
+        s1 = fmaf(float(i + 1), x[i], s1);
+        const float sq = x[i] * x[i];
+        if (i < split) plo += sq; else phi += sq;
+    }
+    float sk = fmaf(float(k0), sx, s1);            // sum (k0 + i + 1) x_i
+    const float part = plo + phi;
+    sx = warp_sum(sx);
+    sk = warp_sum(sk);
+    float incl = part;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    const float sxx = __shfl_sync(0xffffffffu, incl, 31);
+    constexpr float invK = 1.f / float(K);
+    float cen = 0.f, spr = 0.f;
+    if (sx > 0.f) cen = (sk / sx) * invK;
+    // ---- spread, flux, rolloff count in one register pass
+    const float nx = 1.f / (sx + float(K) * B200AA_EPS);
+    const float np_ = 1.f / (sxp + float(K) * B200AA_EPS);
+    const float thr = 0.90f * sxx;
+    const float base = float(k0 + 1) * invK - cen;
+    float sp = 0.f, fl = 0.f, run = incl - part, below = 0.f;
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+        const float d = fmaf(float(i), invK, base);
+        sp = fmaf(d * d, x[i], sp);
+        const float xp = (k0 + i < K) ? Xp[k0 + i] : 0.f;
+        const float df = fmaf(x[i], nx, -xp * np_);
+        fl = fmaf(df, df, fl);
+        run = fmaf(x[i], x[i], run);
+        // cumulative sums are non-decreasing, so the index of the first bin whose cumsum + eps exceeds
+        // the threshold equals the number of bins that do not exceed it (:134-137)
+        below += (k0 + i < K && !(run + B200AA_EPS > thr)) ? 1.f : 0.f;
+    }
+    sp = warp_sum(sp);
+    fl = warp_sum(fl);
+    below = warp_sum(below);
+    if (sx > 0.f) spr = sqrtf(sp / sx);
+    const float roll = below >= float(K) ? 0.f : below * invK;
+    // ---- spectral entropy: block j gathers the lane parts that belong to it
+    float ent = 0.f;
+    {
+        float e = 0.f;
+        // lanes 0..9 own block `lane`: bins [lane*Lb, (lane+1)*Lb) -> lanes A..B
+        const int j = lane < 10 ? lane : 9;
+        const int A = (j * Lb) / C, Bn = ((j + 1) * Lb - 1) / C;
+        constexpr int SPAN = Lb / C + 2;
+#pragma unroll
+        for (int m = 0; m < SPAN; ++m) {
+            const int src = min(A + m, 31);
+            const float vlo = __shfl_sync(0xffffffffu, plo, src);
+            const float vhi = __shfl_sync(0xffffffffu, phi, src);
+            const int sb = __shfl_sync(0xffffffffu, bnd, src);       // boundary bin inside lane src (or <= its k0)
+            if (A + m <= Bn) {
+                // lane src covers [src*C, src*C+C); its "hi" part starts at max(sb, src*C)
+                const int hs = sb > src * C ? sb : src * C;
+                if (hs >= j * Lb && hs < (j + 1) * Lb) e += vhi;     // hi part lies in block j
+                if (sb > src * C && (sb - 1) >= j * Lb && (sb - 1) < (j + 1) * Lb) e += vlo;   // lo part lies in block j
+            }
+        }
+        if (lane < 10) {
+            const float sj = e / (sxx + B200AA_EPS);
+            ent = -sj * log2f(sj + B200AA_EPS);
+        }
+        ent = warp_sum(ent);
+    }
+    // chroma: the 12 raw tap sums of this frame were produced by the flat phase (chroma_raw)
+    const float ch = lane < 12 ? chroma_raw[lane] / (sxx == 0.f ? B200AA_EPS : sxx) : 0.f;
+    const float mean = warp_sum(ch) * (1.f / 12.f);
+    const float dv = lane < 12 ? ch - mean : 0.f;
+    const float var = warp_sum(dv * dv) * (1.f / 12.f);
+    if (lane < 12) fv[21 + lane] = ch;
+    if (lane == 0) {
+        fv[3] = cen; fv[4] = spr; fv[5] = ent; fv[6] = fl; fv[7] = roll;
+        fv[33] = sqrtf(var);
+        *sx_out = sx;
+    }
+    __syncwarp();
+}
+
+// ---- flat phase 1 (all 256 threads, 8 frames): threads 0..159 = (frame, mel filter pair) -> log10 mel
+// energies; threads 160..255 = (frame, pitch class) -> raw chroma tap sums.  Filters are paired
+// long-with-short on the host so every thread sees about the same number of taps.
+__device__ __forceinline__ void flat_mel_chroma(const float *Xrows, int Kp, int ng, const SmallTables &tb,
+                                                const int *pair_tab, float *ms, float *chr, int tid)
+{
+    if (tid < kFastG * 20) {
+        const int f = tid / 20, pr = tid - f * 20;
+        if (f < ng) {
+            const float *X = Xrows + size_t(f) * Kp;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = pair_tab[2 * pr + h];
+                const int s0 = tb.mel_start[i], cnt = tb.mel_count[i], off = tb.mel_off[i];
+                float acc = 0.f;
+                for (int t = 0; t < cnt; ++t) acc = fmaf(X[s0 + t], tb.mel_w[off + t], acc);
+                ms[f * B200AA_N_MEL + i] = log10f(acc + B200AA_EPS);
+            }
+        }
+    } else {
+        const int ct = tid - kFastG * 20;
+        const int f = ct / 12, c = ct - f * 12;
+        if (f < ng) {
+            const float *X = Xrows + size_t(f) * Kp;
+            const int e0 = tb.chr_off[c], e1 = tb.chr_off[c + 1];
+            float acc = 0.f;
+            for (int e = e0; e < e1; ++e) {
+                const float v = X[tb.chr_bin[e]];
+                acc = fmaf(v * v, tb.chr_w[e], acc);
+            }
+            chr[f * 12 + c] = acc;
+        }
+    }
+}
+
+// ---- flat phase 2: threads 0..207 = (frame, cepstral row c, half h): folded DCT-II
+//   y_c = sum_{n<20} D[c][n] * ((m_n - k) + (-1)^c (m_{39-n} - k)),  k = m_0 (any constant works for
+//   c >= 1 because those rows are orthogonal to constants; row 0 adds it back): keeps the float32 sum
+//   free of the large common offset of the log-mel values.
+__device__ __forceinline__ void flat_dct(const float *ms, int ng, const SmallTables &tb, float *fvrows, int tid)
+{
+    const int f = tid / 26, r = tid - f * 26;
+    const int c = r >> 1, h = r & 1;
+    float acc = 0.f;
+    const bool act = tid < kFastG * 26 && f < ng;
+    if (act) {
+        const float *m = ms + f * B200AA_N_MEL;
+        const float kap = m[0];
+        const float *row = tb.dct + c * 41;
+        const float sgn = (c & 1) ? -1.f : 1.f;
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+            const int n = 10 * h + j;
+            const float a = m[n] - kap, b = m[39 - n] - kap;
+            acc = fmaf(row[n], fmaf(sgn, b, a), acc);
+        }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (act && h == 0) {
+        if (c == 0) acc = fmaf(6.324555320336759f, ms[f * B200AA_N_MEL], acc);    // sqrt(1/40) * 40 * k
+        fvrows[size_t(f + 1) * kFvStride + 8 + c] = acc;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// staging fused with the time-domain partials.  One thread converts one run of 8 consecutive
+// samples (one 16-byte load of int16), stores x - m to shared memory and emits for the run:
+//   runE = sum y^2                      (y = a (x-m) + bp, energy / energy-entropy, :29-51)
+//   runF = sign flips inside the run + (flip between the run's first sample and its predecessor) << 8
+// Frames are whole numbers of runs (N % 80 == 0, step % 8 == 0), so zcr / energy / block energies of
+// a frame are sums over its 100 runs and the 50 % overlap is computed once.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sign_class(float d, float lo, float hi) { return (d > lo) - (d < hi); }
+
+__device__ __forceinline__ void stage_run(const void *clip, int dtype, bool vec_ok, int64_t n0, const b200aa_clip_norm &nm,
+                                          float *dst, float *runE, int *runF)
+{
+    float d[8];
+    if (dtype == B200AA_DTYPE_I16) {
+        const short *x = reinterpret_cast<const short *>(clip) + n0;
+        if (vec_ok) {
+            const int4 q = __ldg(reinterpret_cast<const int4 *>(x));
+            const int w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                d[2 * u] = float((short)(w4[u] & 0xffff)) - nm.m;
+                d[2 * u + 1] = float(w4[u] >> 16) - nm.m;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) d[u] = float(x[u]) - nm.m;
+        }
+    } else {
+        const float *x = reinterpret_cast<const float *>(clip) + n0;
+        if (vec_ok) {
+            const float4 q0 = __ldg(reinterpret_cast<const float4 *>(x)), q1 = __ldg(reinterpret_cast<const float4 *>(x) + 1);
+            d[0] = q0.x - nm.m; d[1] = q0.y - nm.m; d[2] = q0.z - nm.m; d[3] = q0.w - nm.m;
+            d[4] = q1.x - nm.m; d[5] = q1.y - nm.m; d[6] = q1.z - nm.m; d[7] = q1.w - nm.m;
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) d[u] = x[u] - nm.m;
+        }
+    }
+    float e = 0.f;
+    int s[8], fl = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const float y = fmaf(nm.a, d[u], nm.bp);
+        e = fmaf(y, y, e);
+        s[u] = sign_class(d[u], nm.lo, nm.hi);
+        if (u > 0) fl += abs(s[u] - s[u - 1]);
+    }
+    int link = 0;
+    if (n0 > 0) {
+        const float dp = (dtype == B200AA_DTYPE_I16 ? float(reinterpret_cast<const short *>(clip)[n0 - 1])
+                                                    : reinterpret_cast<const float *>(clip)[n0 - 1]) - nm.m;
+        link = abs(s[0] - sign_class(dp, nm.lo, nm.hi));
+    }
+    *reinterpret_cast<float4 *>(dst) = make_float4(d[0], d[1], d[2], d[3]);
+    *reinterpret_cast<float4 *>(dst + 4) = make_float4(d[4], d[5], d[6], d[7]);
+    *runE = e;
+    *runF = fl | (link << 8);
+}
+
+// zcr, energy, energy entropy of one frame from its runs (warp; lanes 0..9 own the 10 entropy blocks)
+template <int N>
+__device__ __forceinline__ void time_features_runs(const float *runE, const int *runF, float *fv, int lane)
+{
+    constexpr int RPB = N / 80;            // runs per entropy block (block = N/10 samples = RPB runs)
+    float e = 0.f;
+    int f = 0;
+    if (lane < 10) {
+#pragma unroll
+        for (int i = 0; i < RPB; ++i) {
+            e += runE[lane * RPB + i];
+            const int w = runF[lane * RPB + i];
+            f += (w & 0xff) + (w >> 8);
+        }
+    }
+    const float tot = warp_sum(e);
+    int ft = f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ft += __shfl_xor_sync(0xffffffffu, ft, o);
+    ft -= runF[0] >> 8;                    // the pair (frame start - 1, frame start) is not part of the frame
+    const float sj = e / (tot + B200AA_EPS);
+    float H = lane < 10 ? -sj * log2f(sj + B200AA_EPS) : 0.f;
+    H = warp_sum(H);
+    if (lane == 0) {
+        fv[0] = float(ft) * 0.5f / float(N - 1);
+        fv[1] = tot / float(N);
+        fv[2] = H;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
 // kernel
 // ----------------------------------------------------------------------------------------------
 struct FastTables {
@@ -159,7 +421,6 @@ struct FastTables {
     }
 };
 
-constexpr int kFastG = 8;   // frames per CTA step
 
 template <int R>
 struct FastShape {
@@ -180,14 +441,15 @@ inline size_t fast_smem_bytes(int step, int blob_words)
     b += size_t(kFastG) * S::ZS * sizeof(float2);                         // published second-pass outputs
     b += size_t(S::Kp) * sizeof(float);                                   // |X| of the previous frame
     b += size_t(kFastG + 1) * kFvStride * sizeof(float);
-    b += size_t(kWarps) * B200AA_N_MEL * sizeof(float);
+    b += size_t(kFastG) * (B200AA_N_MEL + 12) * sizeof(float);
     b += size_t(kFastG + 1) * sizeof(float) + 16;
+    b += 2 * size_t(((kFastG - 1) * step + S::N) / 8 + 1) * sizeof(float);   // run partials
     b += size_t(R) * R * sizeof(float2) + size_t(S::Nc / 2 + 1) * sizeof(float2);
     b += size_t(blob_words) * sizeof(int);
     return (b + 15) & ~size_t(15);
 }
 
-template <int R, bool STEP_EVEN>
+template <int R, bool STEP_EVEN, bool RUNS>
 __global__ void __launch_bounds__(kThreads, 2) st_fast_kernel(const StParams p, const float2 *__restrict__ g_tw,
                                                                 const float2 *__restrict__ g_twp)
 {
@@ -203,9 +465,12 @@ __global__ void __launch_bounds__(kThreads, 2) st_fast_kernel(const StParams p, 
     float *sS = reinterpret_cast<float *>(s_twp + (Nc / 2 + 1));             // sample span (8-byte aligned)
     float *Xprev = sS + ((span_max + 4) & ~3);                               // [Kp]
     float *fvrows = Xprev + Kp;                                              // [(G+1)][36]
-    float *mscr = fvrows + (G + 1) * kFvStride;
-    float *rowsum = mscr + kWarps * B200AA_N_MEL;
-    int *blob_s = reinterpret_cast<int *>(rowsum + (G + 1) + 3);
+    float *mscr = fvrows + (G + 1) * kFvStride;                                // [G][40] log-mel energies
+    float *chr = mscr + G * B200AA_N_MEL;                                      // [G][12] raw chroma sums
+    float *rowsum = chr + G * 12;
+    float *runE = rowsum + (G + 1) + 3;                                       // [span_max/8] (RUNS only)
+    int *runF = reinterpret_cast<int *>(runE + (RUNS ? span_max / 8 + 1 : 0));
+    int *blob_s = runF + (RUNS ? span_max / 8 + 1 : 0);
     float *Xrows = reinterpret_cast<float *>(E);                             // rows f -> Xrows + f*Kp (aliases E)
     static_assert(size_t(G) * Kp * sizeof(float) <= size_t(G) * R * ES * sizeof(float2), "alias");
 
@@ -230,13 +495,33 @@ __global__ void __launch_bounds__(kThreads, 2) st_fast_kernel(const StParams p, 
                            size_t(b) * p.clip_stride * (p.dtype == B200AA_DTYPE_I16 ? 2 : 4);
         const SampleReader rd{clip, p.dtype, nm.m};
         const int halo = int(t0 < 2 ? t0 : 2);
+        // 16-byte loads need the clip base and the step's first sample aligned (8 samples of int16)
+        const bool vec_ok = (reinterpret_cast<uintptr_t>(clip) & 15) == 0 && (p.dtype == B200AA_DTYPE_I16 || (step % 4 == 0));
 
         for (int64_t g0 = t0 - halo; g0 < t1; g0 += G) {
             const int ng = int((t1 - g0) < G ? (t1 - g0) : G);
             // ---- stage the sample span of this step as float (x - m)
             const int span = (ng - 1) * step + N;
             const int64_t sbase = g0 * step;
-            for (int i = tid; i < span; i += kThreads) sS[i] = rd(sbase + i);
+            if (RUNS) {
+                // samples shared with the previous step are already converted: move them to the front
+                int keep = 0;
+                if (g0 > t0 - halo && step < N) {
+                    keep = N - step;                       // previous step was a full one (G frames)
+                    float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float ce = 0.f; int cf = 0;
+                    const int src = G * step;
+                    if (tid < keep / 4) cv = *reinterpret_cast<const float4 *>(sS + src + 4 * tid);
+                    if (tid < keep / 8) { ce = runE[src / 8 + tid]; cf = runF[src / 8 + tid]; }
+                    __syncthreads();
+                    if (tid < keep / 4) *reinterpret_cast<float4 *>(sS + 4 * tid) = cv;
+                    if (tid < keep / 8) { runE[tid] = ce; runF[tid] = cf; }
+                }
+                for (int r = keep / 8 + tid; r < span / 8; r += kThreads)
+                    stage_run(clip, p.dtype, vec_ok, sbase + 8 * r, nm, sS + 8 * r, runE + r, runF + r);
+            } else {
+                for (int i = tid; i < span; i += kThreads) sS[i] = rd(sbase + i);
+            }
             __syncthreads();
 
             // ---- pass 1: thread (frame ff, column n2 = fj): FFT over n1 of z[R*n1 + n2], twiddle, transpose
@@ -309,7 +594,10 @@ __global__ void __launch_bounds__(kThreads, 2) st_fast_kernel(const StParams p, 
             }
             __syncthreads();
 
-            // ---- features: one warp per frame
+            // ---- flat phase: mel + log10 / raw chroma over all 8 frames, then DCT rows; dense features per warp
+            flat_mel_chroma(Xrows, Kp, ng, tb, blob_s + p.bl.mel_pairs, mscr, chr, tid);
+            __syncthreads();
+            flat_dct(mscr, ng, tb, fvrows, tid);
             for (int f = warp; f < ng; f += kWarps) {
                 const int64_t fr = g0 + f;
                 const float *X = Xrows + size_t(f) * Kp;
@@ -318,7 +606,8 @@ __global__ void __launch_bounds__(kThreads, 2) st_fast_kernel(const StParams p, 
                 const float *Xp;
                 float *fv = fvrows + size_t(f + 1) * kFvStride;
                 const float *frs = sS + f * step;
-                time_features([&](int n) { return frs[n]; }, N, nm, fv, lane);
+                if (RUNS) time_features_runs<N>(runE + (f * step) / 8, runF + (f * step) / 8, fv, lane);
+                else time_features([&](int n) { return frs[n]; }, N, nm, fv, lane);
                 if (has_prev && f > 0) {
                     Xp = Xrows + size_t(f - 1) * Kp;
                     float s = 0.f;
@@ -333,7 +622,7 @@ __global__ void __launch_bounds__(kThreads, 2) st_fast_kernel(const StParams p, 
                     for (int k = lane; k < K; k += 32) s += X[k];
                     sxp = warp_sum(s);
                 }
-                spectral_features(X, Xp, sxp, K, tb, mscr + warp * B200AA_N_MEL, fv, lane, rowsum + f + 1);
+                spectral_features_k<K>(X, Xp, sxp, chr + f * 12, fv, lane, rowsum + f + 1);
             }
             __syncthreads();
             // ---- store [n_out x ng] tile: consecutive threads -> consecutive frames
@@ -397,12 +686,12 @@ inline int fast_plan_init(int fs, int window, int step, const std::vector<int> &
     return B200AA_OK;
 }
 
-template <int R, bool EVEN>
+template <int R, bool EVEN, bool RUNS>
 inline int fast_launch_t(const FastTables &ft, StParams p, int sm_count, int64_t T, cudaStream_t st)
 {
     const size_t smem = fast_smem_bytes<R>(p.step, p.bl.words);
     if (smem > 110u * 1024u) return B200AA_ERR_UNSUPPORTED;      // very large hop: leave it to the generic kernel
-    auto kern = st_fast_kernel<R, EVEN>;
+    auto kern = st_fast_kernel<R, EVEN, RUNS>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200AA_ERR_CUDA;
     int occ = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem) != cudaSuccess) return B200AA_ERR_CUDA;
@@ -424,8 +713,13 @@ inline int fast_launch_t(const FastTables &ft, StParams p, int sm_count, int64_t
 inline int fast_launch_features(int kind, const FastTables &ft, const StParams &p, int sm_count, int64_t T, cudaStream_t st)
 {
     const bool even = (p.step % 2) == 0;
-    if (kind == 20) return even ? fast_launch_t<20, true>(ft, p, sm_count, T, st) : fast_launch_t<20, false>(ft, p, sm_count, T, st);
-    if (kind == 21) return even ? fast_launch_t<21, true>(ft, p, sm_count, T, st) : fast_launch_t<21, false>(ft, p, sm_count, T, st);
+    if (kind == 20) {
+        // whole 8-sample runs per frame and per hop: fused staging + time-domain partials
+        const bool runs = (p.step % 8) == 0 && (p.clip_stride % 8) == 0;
+        if (runs) return fast_launch_t<20, true, true>(ft, p, sm_count, T, st);
+        return even ? fast_launch_t<20, true, false>(ft, p, sm_count, T, st) : fast_launch_t<20, false, false>(ft, p, sm_count, T, st);
+    }
+    if (kind == 21) return even ? fast_launch_t<21, true, false>(ft, p, sm_count, T, st) : fast_launch_t<21, false, false>(ft, p, sm_count, T, st);
     return B200AA_ERR_UNSUPPORTED;
 }
 
