@@ -151,6 +151,19 @@ __device__ __forceinline__ void fft_r(float2 (&v)[R]) { fft_pfa<RFactors<R>::A, 
 // consecutive bins in registers (odd stride => conflict-free loads) and all dense reductions run
 // on those registers.  Same arithmetic as spectral_features() in common.cuh.
 // ----------------------------------------------------------------------------------------------
+// plain sum of a |X| row in exactly the order spectral_features_k uses (lane chunks, then butterfly),
+// so a frame's flux is bit-identical no matter where the frame sits inside a CTA step
+template <int K>
+__device__ __forceinline__ float row_sum_k(const float *X, int lane)
+{
+    constexpr int C = ((K + 31) / 32) | 1;
+    const int k0 = lane * C;
+    float sx = 0.f;
+#pragma unroll
+    for (int i = 0; i < C; ++i) sx += (k0 + i < K) ? X[k0 + i] : 0.f;
+    return warp_sum(sx);
+}
+
 template <int K>
 __device__ __forceinline__ void spectral_features_k(const float *X, const float *Xp, float sxp, const float *chroma_raw,
                                                     float *fv, int lane, float *sx_out)
@@ -435,18 +448,19 @@ template <int R>
 inline size_t fast_smem_bytes(int step, int blob_words)
 {
     using S = FastShape<R>;
+    const size_t span_max = size_t(kFastG - 1) * step + S::N;
+    auto up = [](size_t b) { return (b + 15) & ~size_t(15); };
     size_t b = 0;
-    b += size_t((kFastG - 1) * step + S::N + 4) * sizeof(float);          // sample span
-    b += size_t(kFastG) * R * S::ES * sizeof(float2);                     // transpose buffer (rows 1..8 of |X| alias it)
-    b += size_t(kFastG) * S::ZS * sizeof(float2);                         // published second-pass outputs
-    b += size_t(S::Kp) * sizeof(float);                                   // |X| of the previous frame
-    b += size_t(kFastG + 1) * kFvStride * sizeof(float);
-    b += size_t(kFastG) * (B200AA_N_MEL + 12) * sizeof(float);
-    b += size_t(kFastG + 1) * sizeof(float) + 16;
-    b += 2 * size_t(((kFastG - 1) * step + S::N) / 8 + 1) * sizeof(float);   // run partials
-    b += size_t(R) * R * sizeof(float2) + size_t(S::Nc / 2 + 1) * sizeof(float2);
-    b += size_t(blob_words) * sizeof(int);
-    return (b + 15) & ~size_t(15);
+    b += up(sizeof(float2) * kFastG * R * S::ES);          // transpose buffer (the |X| rows alias it)
+    b += up(sizeof(float2) * kFastG * S::ZS);              // published second-pass outputs
+    b += up(sizeof(float2) * R * R) + up(sizeof(float2) * (S::Nc / 2 + 1));
+    b += up(sizeof(float) * (span_max + 4));               // sample span
+    b += up(sizeof(float) * S::Kp);                        // |X| of the previous frame
+    b += up(sizeof(float) * (kFastG + 1) * kFvStride);
+    b += up(sizeof(float) * kFastG * B200AA_N_MEL) + up(sizeof(float) * kFastG * 12) + up(sizeof(float) * (kFastG + 1));
+    b += 2 * up(sizeof(float) * (span_max / 8 + 1));       // run partials
+    b += up(sizeof(int) * blob_words);
+    return b;
 }
 
 template <int R, bool STEP_EVEN, bool RUNS>
@@ -458,19 +472,22 @@ __global__ void __launch_bounds__(kThreads, 2) st_fast_kernel(const StParams p, 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int step = p.step;
     const int span_max = (G - 1) * step + N;
-    float2 *E = reinterpret_cast<float2 *>(smem_raw);                       // [G][R][ES]
-    float2 *Zs = E + size_t(G) * R * ES;                                      // [G][ZS]
-    float2 *s_tw = Zs + size_t(G) * ZS;                                       // [R][R]
-    float2 *s_twp = s_tw + R * R;                                             // [Nc/2+1]
-    float *sS = reinterpret_cast<float *>(s_twp + (Nc / 2 + 1));             // sample span (8-byte aligned)
-    float *Xprev = sS + ((span_max + 4) & ~3);                               // [Kp]
-    float *fvrows = Xprev + Kp;                                              // [(G+1)][36]
-    float *mscr = fvrows + (G + 1) * kFvStride;                                // [G][40] log-mel energies
-    float *chr = mscr + G * B200AA_N_MEL;                                      // [G][12] raw chroma sums
-    float *rowsum = chr + G * 12;
-    float *runE = rowsum + (G + 1) + 3;                                       // [span_max/8] (RUNS only)
-    int *runF = reinterpret_cast<int *>(runE + (RUNS ? span_max / 8 + 1 : 0));
-    int *blob_s = runF + (RUNS ? span_max / 8 + 1 : 0);
+    // carve shared memory; every array starts on a 16-byte boundary (float4 / float2 accesses)
+    unsigned char *sp_ = smem_raw;
+    auto carve = [&](size_t bytes) { unsigned char *q = sp_; sp_ += (bytes + 15) & ~size_t(15); return q; };
+    float2 *E = reinterpret_cast<float2 *>(carve(sizeof(float2) * G * R * ES));         // [G][R][ES]
+    float2 *Zs = reinterpret_cast<float2 *>(carve(sizeof(float2) * G * ZS));            // [G][ZS]
+    float2 *s_tw = reinterpret_cast<float2 *>(carve(sizeof(float2) * R * R));           // [R][R]
+    float2 *s_twp = reinterpret_cast<float2 *>(carve(sizeof(float2) * (Nc / 2 + 1)));   // [Nc/2+1]
+    float *sS = reinterpret_cast<float *>(carve(sizeof(float) * (span_max + 4)));       // sample span
+    float *Xprev = reinterpret_cast<float *>(carve(sizeof(float) * Kp));                // |X| of the previous frame
+    float *fvrows = reinterpret_cast<float *>(carve(sizeof(float) * (G + 1) * kFvStride));
+    float *mscr = reinterpret_cast<float *>(carve(sizeof(float) * G * B200AA_N_MEL));   // [G][40] log-mel energies
+    float *chr = reinterpret_cast<float *>(carve(sizeof(float) * G * 12));              // [G][12] raw chroma sums
+    float *rowsum = reinterpret_cast<float *>(carve(sizeof(float) * (G + 1)));
+    float *runE = reinterpret_cast<float *>(carve(sizeof(float) * (span_max / 8 + 1)));  // run partials (RUNS only)
+    int *runF = reinterpret_cast<int *>(carve(sizeof(int) * (span_max / 8 + 1)));
+    int *blob_s = reinterpret_cast<int *>(carve(sizeof(int) * p.bl.words));
     float *Xrows = reinterpret_cast<float *>(E);                             // rows f -> Xrows + f*Kp (aliases E)
     static_assert(size_t(G) * Kp * sizeof(float) <= size_t(G) * R * ES * sizeof(float2), "alias");
 
@@ -610,17 +627,13 @@ __global__ void __launch_bounds__(kThreads, 2) st_fast_kernel(const StParams p, 
                 else time_features([&](int n) { return frs[n]; }, N, nm, fv, lane);
                 if (has_prev && f > 0) {
                     Xp = Xrows + size_t(f - 1) * Kp;
-                    float s = 0.f;
-                    for (int k = lane; k < K; k += 32) s += Xp[k];
-                    sxp = warp_sum(s);
+                    sxp = row_sum_k<K>(Xp, lane);      // the neighbour's warp produces its own copy concurrently
                 } else if (has_prev) {
                     Xp = Xprev;
                     sxp = rowsum[0];
                 } else {
                     Xp = X;
-                    float s = 0.f;
-                    for (int k = lane; k < K; k += 32) s += X[k];
-                    sxp = warp_sum(s);
+                    sxp = row_sum_k<K>(X, lane);
                 }
                 spectral_features_k<K>(X, Xp, sxp, chr + f * 12, fv, lane, rowsum + f + 1);
             }

@@ -139,6 +139,9 @@ def test_batch_and_ragged(P):
     assert out.shape == (5, 68, 79) and out.dtype == torch.float32 and out.is_cuda
     for i in range(5):
         check_features(out[i].cpu().numpy(), O.feature_extraction(clips[i], 16000, 800, 400)[0], 400, f"batch clip {i}")
+    # the work split (frames per CTA run, halo recomputation) depends on the batch size; results must not
+    alone = P.feature_extraction_batch(d[2:3], 16000, 800, 400)
+    assert torch.equal(alone[0], out[2]), "result depends on how the batch was split across CTAs"
     lens = torch.tensor([32000, 800, 12345, 31999, 20000], dtype=torch.int64, device="cuda")
     out = P.feature_extraction_batch(d, 16000, 800, 400, lengths=lens)
     for i, L in enumerate(lens.tolist()):
