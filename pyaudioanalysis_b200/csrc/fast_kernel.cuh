@@ -13,7 +13,12 @@
 
 namespace b200aa {
 
-constexpr int kFastG = 8;   // frames per CTA step
+#ifndef B200AA_FAST_G
+#define B200AA_FAST_G 8       // frames per CTA step (CTA = 32*G threads, one warp per frame)
+#endif
+#ifndef B200AA_FAST_MINBLOCKS
+#define B200AA_FAST_MINBLOCKS 3   // CTAs per SM the fast kernel is compiled for (register budget)
+#endif
 
 // ----------------------------------------------------------------------------------------------
 // compile-time trigonometry (exact argument reduction in turns, Taylor series in double)
@@ -151,46 +156,111 @@ __device__ __forceinline__ void fft_r(float2 (&v)[R]) { fft_pfa<RFactors<R>::A, 
 // consecutive bins in registers (odd stride => conflict-free loads) and all dense reductions run
 // on those registers.  Same arithmetic as spectral_features() in common.cuh.
 // ----------------------------------------------------------------------------------------------
+// ---- cheap math: MUFU-based reciprocal / rsqrt / log2 (2 ulp); the parity tolerance is 1e-4
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float fsqrt_pos(float x) { return x * rsqrtf(fmaxf(x, 1e-36f)); }   // 0 -> 0
+__device__ __forceinline__ float flog2(float x) { return __log2f(x); }
+
+// two sums with 5 exchanges + 2 broadcasts (instead of 10 exchanges)
+__device__ __forceinline__ void warp_sum2(float &a, float &b, int lane)
+{
+    const bool up = lane & 16;
+    float keep = up ? b : a;
+    const float give = up ? a : b;
+    keep += __shfl_xor_sync(0xffffffffu, give, 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+    a = __shfl_sync(0xffffffffu, keep, 0);
+    b = __shfl_sync(0xffffffffu, keep, 16);
+}
+// four sums with 5 exchanges; the totals end up in lanes 0 (a), 8 (b), 16 (c), 24 (d) -- and in every
+// lane of the same 8-lane group
+__device__ __forceinline__ float warp_sum4_grouped(float a, float b, float c, float d, int lane)
+{
+    const bool up16 = lane & 16, up8 = lane & 8;
+    // first exchange: lower half keeps (a, b), upper half keeps (c, d)
+    float k0 = up16 ? c : a, k1 = up16 ? d : b;
+    const float g0 = up16 ? a : c, g1 = up16 ? b : d;
+    k0 += __shfl_xor_sync(0xffffffffu, g0, 16);
+    k1 += __shfl_xor_sync(0xffffffffu, g1, 16);
+    // second exchange: within each half, lower quarter keeps k0, upper quarter keeps k1
+    float k = up8 ? k1 : k0;
+    const float g = up8 ? k0 : k1;
+    k += __shfl_xor_sync(0xffffffffu, g, 8);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) k += __shfl_xor_sync(0xffffffffu, k, o);
+    return k;
+}
+
+template <int K>
+struct DenseShape {
+    static constexpr int C = ((K + 31) / 32) | 1;   // bins per lane (odd => conflict-free chunk loads)
+    static constexpr int Kp = 32 * C;               // row length incl. zero padding: no bounds checks
+    static constexpr int Lb = K / 10;               // spectral-entropy block length (:94)
+};
+
 // plain sum of a |X| row in exactly the order spectral_features_k uses (lane chunks, then butterfly),
 // so a frame's flux is bit-identical no matter where the frame sits inside a CTA step
 template <int K>
 __device__ __forceinline__ float row_sum_k(const float *X, int lane)
 {
-    constexpr int C = ((K + 31) / 32) | 1;
+    constexpr int C = DenseShape<K>::C;
     const int k0 = lane * C;
     float sx = 0.f;
 #pragma unroll
-    for (int i = 0; i < C; ++i) sx += (k0 + i < K) ? X[k0 + i] : 0.f;
+    for (int i = 0; i < C; ++i) sx += X[k0 + i];
     return warp_sum(sx);
+}
+
+// per-lane constants of the dense pass (depend on the lane only; computed once per CTA)
+struct DenseLane {
+    int split;        // bins [0, split) of the lane's chunk belong to the previous entropy block
+    int ps, pe;       // lanes 0..9: range of "parts" (2 per lane, in bin order) that make up block `lane`
+};
+template <int K>
+__device__ __forceinline__ DenseLane dense_lane_init(int lane)
+{
+    constexpr int C = DenseShape<K>::C, Lb = DenseShape<K>::Lb;
+    static_assert(C < Lb, "a lane may straddle at most one entropy block boundary");
+    DenseLane d;
+    const int k0 = lane * C;
+    const int bnd = ((k0 + C - 1) / Lb) * Lb;
+    d.split = bnd > k0 ? bnd - k0 : 0;
+    d.ps = 64; d.pe = 0;
+    const int j = lane;
+    for (int l = 0; l < 32; ++l) {
+        const int b0 = l * C, bb = ((b0 + C - 1) / Lb) * Lb, sp = bb > b0 ? bb - b0 : 0;
+        // part 2l = [b0, b0+sp), part 2l+1 = [b0+sp, b0+C)
+        if (sp > 0 && b0 >= j * Lb && b0 + sp <= (j + 1) * Lb) { d.ps = min(d.ps, 2 * l); d.pe = max(d.pe, 2 * l + 1); }
+        if (b0 + sp >= j * Lb && b0 + C <= (j + 1) * Lb) { d.ps = min(d.ps, 2 * l + 1); d.pe = max(d.pe, 2 * l + 2); }
+    }
+    if (lane >= 10) { d.ps = 0; d.pe = 0; }
+    return d;
 }
 
 template <int K>
 __device__ __forceinline__ void spectral_features_k(const float *X, const float *Xp, float sxp, const float *chroma_raw,
-                                                    float *fv, int lane, float *sx_out)
+                                                    const DenseLane &dl, float *parts, float *fv, int lane, float *sx_out)
 {
-    constexpr int C = ((K + 31) / 32) | 1;
-    constexpr int Lb = K / 10;                     // spectral-entropy block length (:94)
+    constexpr int C = DenseShape<K>::C;
     const int k0 = lane * C;
     float x[C];
 #pragma unroll
-    for (int i = 0; i < C; ++i) x[i] = (k0 + i < K) ? X[k0 + i] : 0.f;
-    // ---- sums: sum X, sum (k+1) X, sum X^2 (with the part below / above an entropy-block boundary)
-    // the single multiple of Lb that can fall inside (k0, k0 + C): C < Lb
-    static_assert(C < Lb, "a lane may straddle at most one entropy block boundary");
-    const int bnd = ((k0 + C - 1) / Lb) * Lb;      // first bin of the block that contains the lane's last bin
-    const int split = bnd > k0 ? bnd - k0 : 0;     // bins [0, split) belong to the previous block
+    for (int i = 0; i < C; ++i) x[i] = X[k0 + i];
+    // ---- sums: sum X, sum (k+1) X, sum X^2 split at the entropy-block boundary inside the chunk
     float sx = 0.f, s1 = 0.f, plo = 0.f, phi = 0.f;
 #pragma unroll
     for (int i = 0; i < C; ++i) {
         sx += x[i];
         s1 = fmaf(float(i + 1), x[i], s1);
         const float sq = x[i] * x[i];
-        if (i < split) plo += sq; else phi += sq;
+        if (i < dl.split) plo += sq; else phi += sq;
     }
     float sk = fmaf(float(k0), sx, s1);            // sum (k0 + i + 1) x_i
     const float part = plo + phi;
-    sx = warp_sum(sx);
-    sk = warp_sum(sk);
+    parts[2 * lane] = plo;
+    parts[2 * lane + 1] = phi;
+    warp_sum2(sx, sk, lane);
     float incl = part;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -199,79 +269,61 @@ __device__ __forceinline__ void spectral_features_k(const float *X, const float 
     }
     const float sxx = __shfl_sync(0xffffffffu, incl, 31);
     constexpr float invK = 1.f / float(K);
-    float cen = 0.f, spr = 0.f;
-    if (sx > 0.f) cen = (sk / sx) * invK;
+    const float cen = sx > 0.f ? fdiv(sk, sx) * invK : 0.f;
     // ---- spread, flux, rolloff count in one register pass
-    const float nx = 1.f / (sx + float(K) * B200AA_EPS);
-    const float np_ = 1.f / (sxp + float(K) * B200AA_EPS);
-    const float thr = 0.90f * sxx;
+    const float nx = fdiv(1.f, sx + float(K) * B200AA_EPS);
+    const float np_ = fdiv(1.f, sxp + float(K) * B200AA_EPS);
+    const float thr = 0.90f * sxx - B200AA_EPS;    // cumsum + eps > 0.9 E  <=>  cumsum > 0.9 E - eps
     const float base = float(k0 + 1) * invK - cen;
     float sp = 0.f, fl = 0.f, run = incl - part, below = 0.f;
 #pragma unroll
     for (int i = 0; i < C; ++i) {
         const float d = fmaf(float(i), invK, base);
         sp = fmaf(d * d, x[i], sp);
-        const float xp = (k0 + i < K) ? Xp[k0 + i] : 0.f;
-        const float df = fmaf(x[i], nx, -xp * np_);
+        const float df = fmaf(x[i], nx, -Xp[k0 + i] * np_);
         fl = fmaf(df, df, fl);
         run = fmaf(x[i], x[i], run);
-        // cumulative sums are non-decreasing, so the index of the first bin whose cumsum + eps exceeds
-        // the threshold equals the number of bins that do not exceed it (:134-137)
-        below += (k0 + i < K && !(run + B200AA_EPS > thr)) ? 1.f : 0.f;
+        // cumulative sums are non-decreasing, so the index of the first bin whose cumsum + eps exceeds the
+        // threshold equals the number of (real) bins that do not exceed it (:134-137); padding bins never count
+        below += (run > thr || k0 + i >= K) ? 0.f : 1.f;
     }
-    sp = warp_sum(sp);
-    fl = warp_sum(fl);
-    below = warp_sum(below);
-    if (sx > 0.f) spr = sqrtf(sp / sx);
-    const float roll = below >= float(K) ? 0.f : below * invK;
-    // ---- spectral entropy: block j gathers the lane parts that belong to it
+    // ---- spectral entropy: lanes 0..9 add up the parts of their block (parts are in bin order)
+    __syncwarp();
+    float e = 0.f;
+    for (int q = dl.ps; q < dl.pe; ++q) e += parts[q];
     float ent = 0.f;
-    {
-        float e = 0.f;
-        // lanes 0..9 own block `lane`: bins [lane*Lb, (lane+1)*Lb) -> lanes A..B
-        const int j = lane < 10 ? lane : 9;
-        const int A = (j * Lb) / C, Bn = ((j + 1) * Lb - 1) / C;
-        constexpr int SPAN = Lb / C + 2;
-#pragma unroll
-        for (int m = 0; m < SPAN; ++m) {
-            const int src = min(A + m, 31);
-            const float vlo = __shfl_sync(0xffffffffu, plo, src);
-            const float vhi = __shfl_sync(0xffffffffu, phi, src);
-            const int sb = __shfl_sync(0xffffffffu, bnd, src);       // boundary bin inside lane src (or <= its k0)
-            if (A + m <= Bn) {
-                // lane src covers [src*C, src*C+C); its "hi" part starts at max(sb, src*C)
-                const int hs = sb > src * C ? sb : src * C;
-                if (hs >= j * Lb && hs < (j + 1) * Lb) e += vhi;     // hi part lies in block j
-                if (sb > src * C && (sb - 1) >= j * Lb && (sb - 1) < (j + 1) * Lb) e += vlo;   // lo part lies in block j
-            }
-        }
-        if (lane < 10) {
-            const float sj = e / (sxx + B200AA_EPS);
-            ent = -sj * log2f(sj + B200AA_EPS);
-        }
-        ent = warp_sum(ent);
+    if (lane < 10) {
+        const float sj = fdiv(e, sxx + B200AA_EPS);
+        ent = -sj * flog2(sj + B200AA_EPS);
     }
     // chroma: the 12 raw tap sums of this frame were produced by the flat phase (chroma_raw)
-    const float ch = lane < 12 ? chroma_raw[lane] / (sxx == 0.f ? B200AA_EPS : sxx) : 0.f;
+    const float ch = lane < 12 ? fdiv(chroma_raw[lane], sxx == 0.f ? B200AA_EPS : sxx) : 0.f;
+    // totals: lanes 0-7 spread, 8-15 flux, 16-23 rolloff count, 24-31 entropy
+    const float q4 = warp_sum4_grouped(sp, fl, below, ent, lane);
     const float mean = warp_sum(ch) * (1.f / 12.f);
     const float dv = lane < 12 ? ch - mean : 0.f;
     const float var = warp_sum(dv * dv) * (1.f / 12.f);
     if (lane < 12) fv[21 + lane] = ch;
     if (lane == 0) {
-        fv[3] = cen; fv[4] = spr; fv[5] = ent; fv[6] = fl; fv[7] = roll;
-        fv[33] = sqrtf(var);
+        fv[3] = cen;
+        fv[4] = sx > 0.f ? fsqrt_pos(fdiv(q4, sx)) : 0.f;
+        fv[33] = fsqrt_pos(var);
         *sx_out = sx;
     }
+    if (lane == 8) fv[6] = q4;
+    if (lane == 16) fv[7] = q4 >= float(K) ? 0.f : q4 * invK;
+    if (lane == 24) fv[5] = q4;
     __syncwarp();
 }
 
 // ---- flat phase 1 (all 256 threads, 8 frames): threads 0..159 = (frame, mel filter pair) -> log10 mel
 // energies; threads 160..255 = (frame, pitch class) -> raw chroma tap sums.  Filters are paired
 // long-with-short on the host so every thread sees about the same number of taps.
+template <int G>
 __device__ __forceinline__ void flat_mel_chroma(const float *Xrows, int Kp, int ng, const SmallTables &tb,
                                                 const int *pair_tab, float *ms, float *chr, int tid)
 {
-    if (tid < kFastG * 20) {
+    if (tid < G * 20) {
         const int f = tid / 20, pr = tid - f * 20;
         if (f < ng) {
             const float *X = Xrows + size_t(f) * Kp;
@@ -281,11 +333,11 @@ __device__ __forceinline__ void flat_mel_chroma(const float *Xrows, int Kp, int 
                 const int s0 = tb.mel_start[i], cnt = tb.mel_count[i], off = tb.mel_off[i];
                 float acc = 0.f;
                 for (int t = 0; t < cnt; ++t) acc = fmaf(X[s0 + t], tb.mel_w[off + t], acc);
-                ms[f * B200AA_N_MEL + i] = log10f(acc + B200AA_EPS);
+                ms[f * B200AA_N_MEL + i] = 0.30102999566398120f * flog2(acc + B200AA_EPS);   // log10
             }
         }
     } else {
-        const int ct = tid - kFastG * 20;
+        const int ct = tid - G * 20;
         const int f = ct / 12, c = ct - f * 12;
         if (f < ng) {
             const float *X = Xrows + size_t(f) * Kp;
@@ -304,12 +356,13 @@ __device__ __forceinline__ void flat_mel_chroma(const float *Xrows, int Kp, int 
 //   y_c = sum_{n<20} D[c][n] * ((m_n - k) + (-1)^c (m_{39-n} - k)),  k = m_0 (any constant works for
 //   c >= 1 because those rows are orthogonal to constants; row 0 adds it back): keeps the float32 sum
 //   free of the large common offset of the log-mel values.
+template <int G>
 __device__ __forceinline__ void flat_dct(const float *ms, int ng, const SmallTables &tb, float *fvrows, int tid)
 {
     const int f = tid / 26, r = tid - f * 26;
     const int c = r >> 1, h = r & 1;
     float acc = 0.f;
-    const bool act = tid < kFastG * 26 && f < ng;
+    const bool act = tid < G * 26 && f < ng;
     if (act) {
         const float *m = ms + f * B200AA_N_MEL;
         const float kap = m[0];
@@ -337,7 +390,8 @@ __device__ __forceinline__ void flat_dct(const float *ms, int ng, const SmallTab
 // Frames are whole numbers of runs (N % 80 == 0, step % 8 == 0), so zcr / energy / block energies of
 // a frame are sums over its 100 runs and the 50 % overlap is computed once.
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ int sign_class(float d, float lo, float hi) { return (d > lo) - (d < hi); }
+// sign(x - mean) in {-1, 0, +1} as a float, from the exact thresholds of b200aa_clip_norm
+__device__ __forceinline__ float sign_class(float d, float lo, float hi) { return (d > lo ? 1.f : 0.f) - (d < hi ? 1.f : 0.f); }
 
 __device__ __forceinline__ void stage_run(const void *clip, int dtype, bool vec_ok, int64_t n0, const b200aa_clip_norm &nm,
                                           float *dst, float *runE, int *runF)
@@ -368,25 +422,26 @@ __device__ __forceinline__ void stage_run(const void *clip, int dtype, bool vec_
             for (int u = 0; u < 8; ++u) d[u] = x[u] - nm.m;
         }
     }
-    float e = 0.f;
-    int s[8], fl = 0;
+    float e = 0.f, fl = 0.f, s[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
         const float y = fmaf(nm.a, d[u], nm.bp);
         e = fmaf(y, y, e);
         s[u] = sign_class(d[u], nm.lo, nm.hi);
-        if (u > 0) fl += abs(s[u] - s[u - 1]);
+        if (u > 0) fl += fabsf(s[u] - s[u - 1]);
     }
-    int link = 0;
+    float linkf = 0.f;
     if (n0 > 0) {
         const float dp = (dtype == B200AA_DTYPE_I16 ? float(reinterpret_cast<const short *>(clip)[n0 - 1])
                                                     : reinterpret_cast<const float *>(clip)[n0 - 1]) - nm.m;
-        link = abs(s[0] - sign_class(dp, nm.lo, nm.hi));
+        linkf = fabsf(s[0] - sign_class(dp, nm.lo, nm.hi));
     }
+    const int link = int(linkf);
+    const int fli = int(fl);
     *reinterpret_cast<float4 *>(dst) = make_float4(d[0], d[1], d[2], d[3]);
     *reinterpret_cast<float4 *>(dst + 4) = make_float4(d[4], d[5], d[6], d[7]);
     *runE = e;
-    *runF = fl | (link << 8);
+    *runF = fli | (link << 8);
 }
 
 // zcr, energy, energy entropy of one frame from its runs (warp; lanes 0..9 own the 10 entropy blocks)
@@ -409,8 +464,8 @@ __device__ __forceinline__ void time_features_runs(const float *runE, const int 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ft += __shfl_xor_sync(0xffffffffu, ft, o);
     ft -= runF[0] >> 8;                    // the pair (frame start - 1, frame start) is not part of the frame
-    const float sj = e / (tot + B200AA_EPS);
-    float H = lane < 10 ? -sj * log2f(sj + B200AA_EPS) : 0.f;
+    const float sj = fdiv(e, tot + B200AA_EPS);
+    float H = lane < 10 ? -sj * flog2(sj + B200AA_EPS) : 0.f;
     H = warp_sum(H);
     if (lane == 0) {
         fv[0] = float(ft) * 0.5f / float(N - 1);
@@ -435,40 +490,42 @@ struct FastTables {
 };
 
 
-template <int R>
+template <int R, int G>
 struct FastShape {
-    static constexpr int Nc = R * R, N = 2 * Nc, K = Nc, Kp = (K + 3) & ~3;
+    static constexpr int Nc = R * R, N = 2 * Nc, K = Nc, Kp = DenseShape<Nc>::Kp;   // rows zero-padded to 32*C bins
     static constexpr int ES = R | 1;             // padded row stride of the transpose buffer (float2)
     static constexpr int H = R / 2;              // second-pass outputs k2 >= H are published for the partners
     static constexpr int ZS = Nc - R * H;        // published values per frame
-    static constexpr int FftThreads = kFastG * R;
+    static constexpr int FftThreads = G * R;
+    static constexpr int NT = 32 * G;            // threads per CTA
 };
 
-template <int R>
+template <int R, int G>
 inline size_t fast_smem_bytes(int step, int blob_words)
 {
-    using S = FastShape<R>;
-    const size_t span_max = size_t(kFastG - 1) * step + S::N;
+    using S = FastShape<R, G>;
+    const size_t span_max = size_t(G - 1) * step + S::N;
     auto up = [](size_t b) { return (b + 15) & ~size_t(15); };
     size_t b = 0;
-    b += up(sizeof(float2) * kFastG * R * S::ES);          // transpose buffer (the |X| rows alias it)
-    b += up(sizeof(float2) * kFastG * S::ZS);              // published second-pass outputs
+    b += up(sizeof(float2) * G * R * S::ES);          // transpose buffer (the |X| rows alias it)
+    b += up(sizeof(float2) * G * S::ZS);              // published second-pass outputs
     b += up(sizeof(float2) * R * R) + up(sizeof(float2) * (S::Nc / 2 + 1));
     b += up(sizeof(float) * (span_max + 4));               // sample span
     b += up(sizeof(float) * S::Kp);                        // |X| of the previous frame
-    b += up(sizeof(float) * (kFastG + 1) * kFvStride);
-    b += up(sizeof(float) * kFastG * B200AA_N_MEL) + up(sizeof(float) * kFastG * 12) + up(sizeof(float) * (kFastG + 1));
+    b += up(sizeof(float) * (G + 1) * kFvStride);
+    b += up(sizeof(float) * G * B200AA_N_MEL) + up(sizeof(float) * G * 12) + up(sizeof(float) * (G + 1));
+    b += up(sizeof(float) * G * 64);
     b += 2 * up(sizeof(float) * (span_max / 8 + 1));       // run partials
     b += up(sizeof(int) * blob_words);
     return b;
 }
 
-template <int R, bool STEP_EVEN, bool RUNS>
-__global__ void __launch_bounds__(kThreads, 2) st_fast_kernel(const StParams p, const float2 *__restrict__ g_tw,
+template <int R, int G, bool STEP_EVEN, bool RUNS>
+__global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(const StParams p, const float2 *__restrict__ g_tw,
                                                                 const float2 *__restrict__ g_twp)
 {
-    using S = FastShape<R>;
-    constexpr int Nc = S::Nc, N = S::N, K = S::K, Kp = S::Kp, ES = S::ES, H = S::H, ZS = S::ZS, G = kFastG;
+    using S = FastShape<R, G>;
+    constexpr int Nc = S::Nc, N = S::N, K = S::K, Kp = S::Kp, ES = S::ES, H = S::H, ZS = S::ZS, NT = S::NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int step = p.step;
     const int span_max = (G - 1) * step + N;
@@ -485,18 +542,22 @@ __global__ void __launch_bounds__(kThreads, 2) st_fast_kernel(const StParams p, 
     float *mscr = reinterpret_cast<float *>(carve(sizeof(float) * G * B200AA_N_MEL));   // [G][40] log-mel energies
     float *chr = reinterpret_cast<float *>(carve(sizeof(float) * G * 12));              // [G][12] raw chroma sums
     float *rowsum = reinterpret_cast<float *>(carve(sizeof(float) * (G + 1)));
+    float *parts = reinterpret_cast<float *>(carve(sizeof(float) * G * 64));        // entropy parts per warp
     float *runE = reinterpret_cast<float *>(carve(sizeof(float) * (span_max / 8 + 1)));  // run partials (RUNS only)
     int *runF = reinterpret_cast<int *>(carve(sizeof(int) * (span_max / 8 + 1)));
     int *blob_s = reinterpret_cast<int *>(carve(sizeof(int) * p.bl.words));
     float *Xrows = reinterpret_cast<float *>(E);                             // rows f -> Xrows + f*Kp (aliases E)
     static_assert(size_t(G) * Kp * sizeof(float) <= size_t(G) * R * ES * sizeof(float2), "alias");
+    static_assert((G & (G - 1)) == 0 && G * 26 <= NT, "tile mapping");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < p.bl.words; i += kThreads) blob_s[i] = p.blob[i];
-    for (int i = tid; i < R * R; i += kThreads) s_tw[i] = g_tw[i];
-    for (int i = tid; i < Nc / 2 + 1; i += kThreads) s_twp[i] = g_twp[i];
+    for (int i = tid; i < p.bl.words; i += NT) blob_s[i] = p.blob[i];
+    for (int i = tid; i < R * R; i += NT) s_tw[i] = g_tw[i];
+    for (int i = tid; i < Nc / 2 + 1; i += NT) s_twp[i] = g_twp[i];
     __syncthreads();
     const SmallTables tb = bind_tables(blob_s, p.bl);
+    const DenseLane dl = dense_lane_init<K>(lane);
+    for (int i = tid; i < Kp; i += NT) Xprev[i] = 0.f;
     const bool fft_thread = tid < S::FftThreads;
     const int ff = tid / R, fj = tid - ff * R;          // frame slot / index within the frame's R threads
 
@@ -525,19 +586,25 @@ __global__ void __launch_bounds__(kThreads, 2) st_fast_kernel(const StParams p, 
                 int keep = 0;
                 if (g0 > t0 - halo && step < N) {
                     keep = N - step;                       // previous step was a full one (G frames)
-                    float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    float ce = 0.f; int cf = 0;
+                    // up to 2 float4 + 1 run partial per thread (keep <= N - 8 samples)
+                    float4 cv[2];
+                    float ce[1]; int cf[1];
                     const int src = G * step;
-                    if (tid < keep / 4) cv = *reinterpret_cast<const float4 *>(sS + src + 4 * tid);
-                    if (tid < keep / 8) { ce = runE[src / 8 + tid]; cf = runF[src / 8 + tid]; }
+                    static_assert((2 * Nc) / 4 <= 2 * NT && (2 * Nc) / 8 <= NT, "carry copy mapping");
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+                        if (tid + u * NT < keep / 4) cv[u] = *reinterpret_cast<const float4 *>(sS + src + 4 * (tid + u * NT));
+                    if (tid < keep / 8) { ce[0] = runE[src / 8 + tid]; cf[0] = runF[src / 8 + tid]; }
                     __syncthreads();
-                    if (tid < keep / 4) *reinterpret_cast<float4 *>(sS + 4 * tid) = cv;
-                    if (tid < keep / 8) { runE[tid] = ce; runF[tid] = cf; }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+                        if (tid + u * NT < keep / 4) *reinterpret_cast<float4 *>(sS + 4 * (tid + u * NT)) = cv[u];
+                    if (tid < keep / 8) { runE[tid] = ce[0]; runF[tid] = cf[0]; }
                 }
-                for (int r = keep / 8 + tid; r < span / 8; r += kThreads)
+                for (int r = keep / 8 + tid; r < span / 8; r += NT)
                     stage_run(clip, p.dtype, vec_ok, sbase + 8 * r, nm, sS + 8 * r, runE + r, runF + r);
             } else {
-                for (int i = tid; i < span; i += kThreads) sS[i] = rd(sbase + i);
+                for (int i = tid; i < span; i += NT) sS[i] = rd(sbase + i);
             }
             __syncthreads();
 
@@ -584,10 +651,10 @@ __global__ void __launch_bounds__(kThreads, 2) st_fast_kernel(const StParams p, 
                     const float2 ev = make_float2(zk.x + zp.x, zk.y - zp.y);
                     const float2 od = make_float2(zk.y + zp.y, zp.x - zk.x);
                     const float2 t = cmul(od, s_twp[k]);
-                    const float ar = (ev.x + t.x) * sc, ai = (ev.y + t.y) * sc;
-                    const float br = (ev.x - t.x) * sc, bi = (ev.y - t.y) * sc;
-                    Xf[k] = sqrtf(fmaf(ar, ar, ai * ai));
-                    if (do_mirror) Xf[Nc - k] = sqrtf(fmaf(br, br, bi * bi));
+                    const float ar = ev.x + t.x, ai = ev.y + t.y;
+                    const float br = ev.x - t.x, bi = ev.y - t.y;
+                    Xf[k] = fsqrt_pos(fmaf(ar, ar, ai * ai)) * sc;
+                    if (do_mirror) Xf[Nc - k] = fsqrt_pos(fmaf(br, br, bi * bi)) * sc;
                 };
 #pragma unroll
                 for (int k2 = 0; k2 < H; ++k2) {
@@ -604,18 +671,21 @@ __global__ void __launch_bounds__(kThreads, 2) st_fast_kernel(const StParams p, 
                     const int k = fj + R * H;
                     if (2 * k < Nc) pair(k, v[H], true);
                     else if (2 * k == Nc) {          // self-paired bin Nc/2 (R even, thread 0): |X| = |Z|
-                        const float ar = v[H].x * 2.f * sc, ai = v[H].y * 2.f * sc;
-                        Xf[k] = sqrtf(fmaf(ar, ar, ai * ai));
+                        Xf[k] = fsqrt_pos(fmaf(v[H].x, v[H].x, v[H].y * v[H].y)) * (2.f * sc);
                     }
                 }
+            }
+            for (int e = tid; e < G * (Kp - K); e += NT) {     // zero padding of the rows (bins K .. Kp-1)
+                const int f = e / (Kp - K), i = e - f * (Kp - K);
+                Xrows[size_t(f) * Kp + K + i] = 0.f;
             }
             __syncthreads();
 
             // ---- flat phase: mel + log10 / raw chroma over all 8 frames, then DCT rows; dense features per warp
-            flat_mel_chroma(Xrows, Kp, ng, tb, blob_s + p.bl.mel_pairs, mscr, chr, tid);
+            flat_mel_chroma<G>(Xrows, Kp, ng, tb, blob_s + p.bl.mel_pairs, mscr, chr, tid);
             __syncthreads();
-            flat_dct(mscr, ng, tb, fvrows, tid);
-            for (int f = warp; f < ng; f += kWarps) {
+            flat_dct<G>(mscr, ng, tb, fvrows, tid);
+            for (int f = warp; f < ng; f += G) {
                 const int64_t fr = g0 + f;
                 const float *X = Xrows + size_t(f) * Kp;
                 const bool has_prev = (fr > 0) && !(f == 0 && g0 == t0 - halo);
@@ -635,14 +705,14 @@ __global__ void __launch_bounds__(kThreads, 2) st_fast_kernel(const StParams p, 
                     Xp = X;
                     sxp = row_sum_k<K>(X, lane);
                 }
-                spectral_features_k<K>(X, Xp, sxp, chr + f * 12, fv, lane, rowsum + f + 1);
+                spectral_features_k<K>(X, Xp, sxp, chr + f * 12, dl, parts + warp * 64, fv, lane, rowsum + f + 1);
             }
             __syncthreads();
-            // ---- store [n_out x ng] tile: consecutive threads -> consecutive frames
-            for (int e = tid; e < p.n_out * ng; e += kThreads) {
-                const int f = e / ng, c = e - f * ng;
+            // ---- store the [n_out x 8] tile: 8 consecutive threads -> 8 consecutive frames of one feature row
+            for (int e = tid; e < p.n_out * G; e += NT) {
+                const int f = e / G, c = e % G;
                 const int64_t fr = g0 + c;
-                if (fr < t0) continue;
+                if (c >= ng || fr < t0) continue;
                 float val;
                 if (f < B200AA_N_BASE) val = fvrows[size_t(c + 1) * kFvStride + f];
                 else {
@@ -652,7 +722,7 @@ __global__ void __launch_bounds__(kThreads, 2) st_fast_kernel(const StParams p, 
                 p.out[(size_t(b) * p.n_out + f) * p.t_stride + fr] = val;
             }
             // ---- carry the last frame of the step
-            for (int k = tid; k < K; k += kThreads) Xprev[k] = Xrows[size_t(ng - 1) * Kp + k];
+            for (int k = tid; k < K; k += NT) Xprev[k] = Xrows[size_t(ng - 1) * Kp + k];   // padding of Xprev stays 0
             __syncthreads();
             if (tid < kFvStride) fvrows[tid] = fvrows[size_t(ng) * kFvStride + tid];
             if (tid == 0) rowsum[0] = rowsum[ng];
@@ -699,27 +769,28 @@ inline int fast_plan_init(int fs, int window, int step, const std::vector<int> &
     return B200AA_OK;
 }
 
-template <int R, bool EVEN, bool RUNS>
+template <int R, int G, bool EVEN, bool RUNS>
 inline int fast_launch_t(const FastTables &ft, StParams p, int sm_count, int64_t T, cudaStream_t st)
 {
-    const size_t smem = fast_smem_bytes<R>(p.step, p.bl.words);
+    constexpr int NT = 32 * G;
+    const size_t smem = fast_smem_bytes<R, G>(p.step, p.bl.words);
     if (smem > 110u * 1024u) return B200AA_ERR_UNSUPPORTED;      // very large hop: leave it to the generic kernel
-    auto kern = st_fast_kernel<R, EVEN, RUNS>;
+    auto kern = st_fast_kernel<R, G, EVEN, RUNS>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200AA_ERR_CUDA;
     int occ = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem) != cudaSuccess) return B200AA_ERR_CUDA;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem) != cudaSuccess) return B200AA_ERR_CUDA;
     occ = occ < 1 ? 1 : occ;
     const int64_t slots = int64_t(sm_count) * occ;
     int64_t per_clip = (slots * 12 + p.n_clips - 1) / p.n_clips;
     if (per_clip < 1) per_clip = 1;
     int64_t seg = (T + per_clip - 1) / per_clip;
-    if (seg < kFastG * 6 - 2) seg = kFastG * 6 - 2;
+    if (seg < 46) seg = 46;
     if (seg > T) seg = T;
     p.seg_len = seg;
     p.segs_per_clip = (T + seg - 1) / seg;
     p.n_items = p.segs_per_clip * p.n_clips;
     const int64_t grid = p.n_items < slots ? p.n_items : slots;
-    kern<<<(unsigned)grid, kThreads, smem, st>>>(p, ft.d_tw, ft.d_twp);
+    kern<<<(unsigned)grid, NT, smem, st>>>(p, ft.d_tw, ft.d_twp);
     return cudaGetLastError() == cudaSuccess ? B200AA_OK : B200AA_ERR_CUDA;
 }
 
@@ -729,10 +800,10 @@ inline int fast_launch_features(int kind, const FastTables &ft, const StParams &
     if (kind == 20) {
         // whole 8-sample runs per frame and per hop: fused staging + time-domain partials
         const bool runs = (p.step % 8) == 0 && (p.clip_stride % 8) == 0;
-        if (runs) return fast_launch_t<20, true, true>(ft, p, sm_count, T, st);
-        return even ? fast_launch_t<20, true, false>(ft, p, sm_count, T, st) : fast_launch_t<20, false, false>(ft, p, sm_count, T, st);
+        if (runs) return fast_launch_t<20, B200AA_FAST_G, true, true>(ft, p, sm_count, T, st);
+        return even ? fast_launch_t<20, B200AA_FAST_G, true, false>(ft, p, sm_count, T, st) : fast_launch_t<20, B200AA_FAST_G, false, false>(ft, p, sm_count, T, st);
     }
-    if (kind == 21) return even ? fast_launch_t<21, true, false>(ft, p, sm_count, T, st) : fast_launch_t<21, false, false>(ft, p, sm_count, T, st);
+    if (kind == 21) return even ? fast_launch_t<21, B200AA_FAST_G, true, false>(ft, p, sm_count, T, st) : fast_launch_t<21, B200AA_FAST_G, false, false>(ft, p, sm_count, T, st);
     return B200AA_ERR_UNSUPPORTED;
 }
 
