@@ -123,12 +123,12 @@ def mid_feature_extraction_batch(signals, sampling_rate, mid_window, mid_step, s
     return mid_pool_batch(st, ratio, stepr), st
 
 
-def spectrogram_batch(signals, sampling_rate, window, step):
+def spectrogram_batch(signals, sampling_rate, window, step, plan=None):
     """CUDA [B, N] -> CUDA float32 [B, R, K] (ShortTermFeatures.py:389-452 rows, per clip)."""
     window, step = int(window), int(step)
     signals, B, N, stride, _, _ = _prep(signals, None)
     with torch.cuda.device(signals.device):
-        plan = get_plan(sampling_rate, window, step, signals.device.index)
+        plan = plan or get_plan(sampling_rate, window, step, signals.device.index)
         R = lib().b200aa_spectrogram_rows(N, window, step)
         if R <= 0:
             check(_lib.ERR_TOO_SHORT)
@@ -139,12 +139,12 @@ def spectrogram_batch(signals, sampling_rate, window, step):
     return out
 
 
-def chromagram_batch(signals, sampling_rate, window, step):
+def chromagram_batch(signals, sampling_rate, window, step, plan=None):
     """CUDA [B, N] -> CUDA float32 [B, R, 12] (ShortTermFeatures.py:324-386 rows, per clip)."""
     window, step = int(window), int(step)
     signals, B, N, stride, _, _ = _prep(signals, None)
     with torch.cuda.device(signals.device):
-        plan = get_plan(sampling_rate, window, step, signals.device.index)
+        plan = plan or get_plan(sampling_rate, window, step, signals.device.index)
         R = lib().b200aa_chromagram_rows(N, window, step)
         if R <= 0 or N - step - window < 0:
             check(_lib.ERR_TOO_SHORT)

@@ -621,6 +621,11 @@ extern "C" int b200aa_spectrogram(const b200aa_plan *plan, const void *d_sig, in
     p.mode = kModeSpectrogram;
     p.origin = w; p.row0 = 0; p.rows_total = R; p.rows_launch = R;
     p.rows_valid = std::min<int64_t>(R, b200aa_host::range_len(w, n_samples - w + 1, s));   // :415
+    if (pl->fast_kind && !pl->force_generic) {
+        rc = fast_launch_rows(pl->fast_kind, kModeSpectrogram, pl->fast, p, pl->sm_count, static_cast<cudaStream_t>(stream));
+        if (rc == B200AA_OK) { g_launches.fetch_add(1, std::memory_order_relaxed); return rc; }
+        if (rc != B200AA_ERR_UNSUPPORTED) return rc == B200AA_ERR_CUDA ? cuda_fail(cudaGetLastError(), "fast kernel") : rc;
+    }
     return launch_generic<kModeSpectrogram>(pl, p, R, static_cast<cudaStream_t>(stream));
 }
 
@@ -649,7 +654,13 @@ extern "C" int b200aa_chromagram(const b200aa_plan *plan, const void *d_sig, int
     fill_common(p, pl, t, d_sig, dtype, n_clips, n_samples, clip_stride, nullptr, d_norm, d_out);
     p.mode = kModeChromagram;
     p.origin = w; p.row0 = 0; p.rows_total = R; p.rows_launch = R; p.rows_valid = n_full;
-    rc = launch_generic<kModeChromagram>(pl, p, R, st);
+    rc = B200AA_ERR_UNSUPPORTED;
+    if (pl->fast_kind && !pl->force_generic) {
+        rc = fast_launch_rows(pl->fast_kind, kModeChromagram, pl->fast, p, pl->sm_count, st);
+        if (rc == B200AA_OK) g_launches.fetch_add(1, std::memory_order_relaxed);
+        else if (rc != B200AA_ERR_UNSUPPORTED) return rc == B200AA_ERR_CUDA ? cuda_fail(cudaGetLastError(), "fast kernel") : rc;
+    }
+    if (rc == B200AA_ERR_UNSUPPORTED) rc = launch_generic<kModeChromagram>(pl, p, R, st);
     if (rc != B200AA_OK) return rc;
     // frames clipped at the end of the clip: the reference transforms the n < w samples that are
     // left (ShortTermFeatures.py:352-355); fewer than num_fft samples make its scatter raise.

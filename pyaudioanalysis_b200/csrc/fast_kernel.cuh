@@ -480,12 +480,15 @@ __device__ __forceinline__ void time_features_runs(const float *runE, const int 
 struct FastTables {
     float2 *d_tw = nullptr;      // [R][R]   W_Nc^(k1*n2) stored [k1][n2]
     float2 *d_twp = nullptr;     // [Nc/2+1] W_N^k
+    unsigned int *d_counters = nullptr;   // ring of work counters (one per in-flight launch)
+    mutable unsigned int next_counter = 0;
     int R = 0;
     void release()
     {
         if (d_tw) cudaFree(d_tw);
         if (d_twp) cudaFree(d_twp);
-        d_tw = d_twp = nullptr;
+        if (d_counters) cudaFree(d_counters);
+        d_tw = d_twp = nullptr; d_counters = nullptr;
     }
 };
 
@@ -520,9 +523,9 @@ inline size_t fast_smem_bytes(int step, int blob_words)
     return b;
 }
 
-template <int R, int G, bool STEP_EVEN, bool RUNS>
+template <int R, int G, bool STEP_EVEN, bool RUNS, int MODE>
 __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(const StParams p, const float2 *__restrict__ g_tw,
-                                                                const float2 *__restrict__ g_twp)
+                                                                const float2 *__restrict__ g_twp, unsigned int *work_counter)
 {
     using S = FastShape<R, G>;
     constexpr int Nc = S::Nc, N = S::N, K = S::K, Kp = S::Kp, ES = S::ES, H = S::H, ZS = S::ZS, NT = S::NT;
@@ -561,26 +564,44 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
     const bool fft_thread = tid < S::FftThreads;
     const int ff = tid / R, fj = tid - ff * R;          // frame slot / index within the frame's R threads
 
-    for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    // work items are handed out dynamically (one atomic per item) so the tail of the launch is one item long
+    __shared__ unsigned int s_next_item;
+    for (int64_t item = blockIdx.x; item < p.n_items;) {
+        if (tid == 0) s_next_item = atomicAdd(work_counter, 1u) + gridDim.x;
+        do {
         const int64_t b = item / p.segs_per_clip, seg = item % p.segs_per_clip;
         const int64_t len = p.len ? p.len[b] : p.n_samples;
-        const int64_t T = len < N ? 0 : (len - N) / step + 1;
+        // features: frames of the clip; spectrogram / chromagram: the rows of this launch (rows >= n_valid are zero)
+        const int64_t T = MODE == kModeFeatures ? (len < N ? 0 : (len - N) / step + 1) : p.rows_launch;
+        const int64_t n_valid = MODE == kModeFeatures ? T : p.rows_valid;
+        const int64_t origin = MODE == kModeFeatures ? 0 : p.origin;
         const int64_t t0 = seg * p.seg_len;
-        if (t0 >= T) continue;
+        if (t0 >= T) break;
         const int64_t t1 = (t0 + p.seg_len) < T ? (t0 + p.seg_len) : T;
         const b200aa_clip_norm nm = p.norm[b];
         const char *clip = reinterpret_cast<const char *>(p.sig) +
                            size_t(b) * p.clip_stride * (p.dtype == B200AA_DTYPE_I16 ? 2 : 4);
         const SampleReader rd{clip, p.dtype, nm.m};
-        const int halo = int(t0 < 2 ? t0 : 2);
+        const int halo = MODE == kModeFeatures ? int(t0 < 2 ? t0 : 2) : 0;
         // 16-byte loads need the clip base and the step's first sample aligned (8 samples of int16)
         const bool vec_ok = (reinterpret_cast<uintptr_t>(clip) & 15) == 0 && (p.dtype == B200AA_DTYPE_I16 || (step % 4 == 0));
 
         for (int64_t g0 = t0 - halo; g0 < t1; g0 += G) {
-            const int ng = int((t1 - g0) < G ? (t1 - g0) : G);
+            const int nrow = int((t1 - g0) < G ? (t1 - g0) : G);          // rows / frames of this step
+            // frames that exist (spectrogram / chromagram allocate more rows than their loops fill)
+            const int ng = int((n_valid - g0) < nrow ? ((n_valid - g0) > 0 ? (n_valid - g0) : 0) : nrow);
+            if (MODE != kModeFeatures && ng < nrow) {
+                // zero rows (all threads; rows are disjoint from the ones written below)
+                const int width = MODE == kModeSpectrogram ? K : 12;
+                for (int e = tid; e < (nrow - ng) * width; e += NT) {
+                    const int f = ng + e / width, k = e % width;
+                    p.out[(size_t(b) * p.rows_total + p.row0 + g0 + f) * width + k] = 0.f;
+                }
+                if (ng == 0) continue;
+            }
             // ---- stage the sample span of this step as float (x - m)
             const int span = (ng - 1) * step + N;
-            const int64_t sbase = g0 * step;
+            const int64_t sbase = origin + g0 * step;
             if (RUNS) {
                 // samples shared with the previous step are already converted: move them to the front
                 int keep = 0;
@@ -681,6 +702,28 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
             }
             __syncthreads();
 
+            if constexpr (MODE == kModeSpectrogram) {
+                // rows are contiguous in the output: consecutive threads -> consecutive bins
+                float *dst = p.out + (size_t(b) * p.rows_total + p.row0 + g0) * K;
+                for (int e = tid; e < ng * K; e += NT) {
+                    const int f = e / K, k = e - f * K;
+                    dst[e] = Xrows[size_t(f) * Kp + k];
+                }
+                __syncthreads();
+                continue;
+            } else if constexpr (MODE == kModeChromagram) {
+                for (int f = warp; f < ng; f += G) {
+                    const float *X = Xrows + size_t(f) * Kp;
+                    float sxx = 0.f;
+#pragma unroll
+                    for (int i = 0; i < DenseShape<K>::C; ++i) { const float v = X[lane * DenseShape<K>::C + i]; sxx = fmaf(v, v, sxx); }
+                    sxx = warp_sum(sxx);
+                    const float ch = chroma_lane(X, sxx, tb, lane);
+                    if (lane < 12) p.out[(size_t(b) * p.rows_total + p.row0 + g0 + f) * 12 + lane] = ch;
+                }
+                __syncthreads();
+                continue;
+            }
             // ---- flat phase: mel + log10 / raw chroma over all 8 frames, then DCT rows; dense features per warp
             flat_mel_chroma<G>(Xrows, Kp, ng, tb, blob_s + p.bl.mel_pairs, mscr, chr, tid);
             __syncthreads();
@@ -728,6 +771,10 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
             if (tid == 0) rowsum[0] = rowsum[ng];
             __syncthreads();
         }
+        } while (0);
+        __syncthreads();
+        item = s_next_item;
+        __syncthreads();
     }
 }
 
@@ -764,47 +811,68 @@ inline int fast_plan_init(int fs, int window, int step, const std::vector<int> &
     if (cudaMalloc(&ft->d_twp, twp.size() * sizeof(float2)) != cudaSuccess) return B200AA_ERR_CUDA;
     if (cudaMemcpy(ft->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) return B200AA_ERR_CUDA;
     if (cudaMemcpy(ft->d_twp, twp.data(), twp.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) return B200AA_ERR_CUDA;
+    if (cudaMalloc(&ft->d_counters, 64 * sizeof(unsigned int)) != cudaSuccess) return B200AA_ERR_CUDA;
     ft->R = R;
     *kind = R;
     return B200AA_OK;
 }
 
-template <int R, int G, bool EVEN, bool RUNS>
+template <int R, int G, bool EVEN, bool RUNS, int MODE>
 inline int fast_launch_t(const FastTables &ft, StParams p, int sm_count, int64_t T, cudaStream_t st)
 {
     constexpr int NT = 32 * G;
     const size_t smem = fast_smem_bytes<R, G>(p.step, p.bl.words);
     if (smem > 110u * 1024u) return B200AA_ERR_UNSUPPORTED;      // very large hop: leave it to the generic kernel
-    auto kern = st_fast_kernel<R, G, EVEN, RUNS>;
+    auto kern = st_fast_kernel<R, G, EVEN, RUNS, MODE>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200AA_ERR_CUDA;
     int occ = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem) != cudaSuccess) return B200AA_ERR_CUDA;
     occ = occ < 1 ? 1 : occ;
     const int64_t slots = int64_t(sm_count) * occ;
-    int64_t per_clip = (slots * 12 + p.n_clips - 1) / p.n_clips;
+    int64_t per_clip = (slots * 16 + p.n_clips - 1) / p.n_clips;
     if (per_clip < 1) per_clip = 1;
     int64_t seg = (T + per_clip - 1) / per_clip;
-    if (seg < 46) seg = 46;
+    if (seg < 30) seg = 30;        // 4 CTA steps incl. the 2-frame halo: <= 7 % recomputation
     if (seg > T) seg = T;
     p.seg_len = seg;
     p.segs_per_clip = (T + seg - 1) / seg;
     p.n_items = p.segs_per_clip * p.n_clips;
     const int64_t grid = p.n_items < slots ? p.n_items : slots;
-    kern<<<(unsigned)grid, NT, smem, st>>>(p, ft.d_tw, ft.d_twp);
+    unsigned int *ctr = ft.d_counters + (ft.next_counter++ % 64u);
+    if (cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st) != cudaSuccess) return B200AA_ERR_CUDA;
+    kern<<<(unsigned)grid, NT, smem, st>>>(p, ft.d_tw, ft.d_twp, ctr);
     return cudaGetLastError() == cudaSuccess ? B200AA_OK : B200AA_ERR_CUDA;
+}
+
+template <int MODE>
+inline int fast_launch_mode(int kind, const FastTables &ft, const StParams &p, int sm_count, int64_t T, cudaStream_t st)
+{
+    const bool even = (p.step % 2) == 0;
+    constexpr int G = B200AA_FAST_G;
+    if (kind == 20) {
+        // whole 8-sample runs per frame and per hop: fused staging + time-domain partials
+        const bool runs = (p.step % 8) == 0 && (p.clip_stride % 8) == 0 && (p.origin % 8) == 0;
+        if (runs) return fast_launch_t<20, G, true, true, MODE>(ft, p, sm_count, T, st);
+        return even ? fast_launch_t<20, G, true, false, MODE>(ft, p, sm_count, T, st)
+                    : fast_launch_t<20, G, false, false, MODE>(ft, p, sm_count, T, st);
+    }
+    if (kind == 21) {
+        const bool e2 = even && (p.origin % 2) == 0;
+        return e2 ? fast_launch_t<21, G, true, false, MODE>(ft, p, sm_count, T, st)
+                  : fast_launch_t<21, G, false, false, MODE>(ft, p, sm_count, T, st);
+    }
+    return B200AA_ERR_UNSUPPORTED;
 }
 
 inline int fast_launch_features(int kind, const FastTables &ft, const StParams &p, int sm_count, int64_t T, cudaStream_t st)
 {
-    const bool even = (p.step % 2) == 0;
-    if (kind == 20) {
-        // whole 8-sample runs per frame and per hop: fused staging + time-domain partials
-        const bool runs = (p.step % 8) == 0 && (p.clip_stride % 8) == 0;
-        if (runs) return fast_launch_t<20, B200AA_FAST_G, true, true>(ft, p, sm_count, T, st);
-        return even ? fast_launch_t<20, B200AA_FAST_G, true, false>(ft, p, sm_count, T, st) : fast_launch_t<20, B200AA_FAST_G, false, false>(ft, p, sm_count, T, st);
-    }
-    if (kind == 21) return even ? fast_launch_t<21, B200AA_FAST_G, true, false>(ft, p, sm_count, T, st) : fast_launch_t<21, B200AA_FAST_G, false, false>(ft, p, sm_count, T, st);
-    return B200AA_ERR_UNSUPPORTED;
+    return fast_launch_mode<kModeFeatures>(kind, ft, p, sm_count, T, st);
+}
+// spectrogram / chromagram rows of full-length frames (p.origin, p.rows_* filled by the caller)
+inline int fast_launch_rows(int kind, int mode, const FastTables &ft, const StParams &p, int sm_count, cudaStream_t st)
+{
+    if (mode == kModeSpectrogram) return fast_launch_mode<kModeSpectrogram>(kind, ft, p, sm_count, p.rows_launch, st);
+    return fast_launch_mode<kModeChromagram>(kind, ft, p, sm_count, p.rows_launch, st);
 }
 
 }  // namespace b200aa

@@ -182,6 +182,30 @@ def test_kernel_kinds_agree(P):
             check_features(b[i], ref, w // 2, f"generic kernel fs={fs} w={w} s={s}")
 
 
+def test_row_kernels_agree(P):
+    """spectrogram / chromagram through the specialised kernel, the generic kernel and the oracle."""
+    import torch
+    from pyaudioanalysis_b200._lib import Plan
+    for fs, w, s, n in [(16000, 800, 400, 40000), (44100, 882, 441, 50000), (16000, 800, 800, 24000), (16000, 800, 200, 16400)]:
+        clips = np.stack([O.synth_clip(60 + i, n, fs) for i in range(3)])
+        d = torch.from_numpy(clips).cuda()
+        pf, pg = Plan(fs, w, s), Plan(fs, w, s)
+        pg.force_generic(True)
+        for fn, ofn, atol in ((P.spectrogram_batch, O.spectrogram, 1e-7), (P.chromagram_batch, O.chromagram, 1e-6)):
+            a = fn(d, fs, w, s, plan=pf).cpu().numpy()
+            b = fn(d, fs, w, s, plan=pg).cpu().numpy()
+            for i in range(3):
+                ref = ofn(clips[i], fs, w, s)[0]
+                check_close(a[i], ref, f"{fn.__name__} default kernel fs={fs} w={w} s={s}", atol=atol)
+                check_close(b[i], ref, f"{fn.__name__} generic kernel fs={fs} w={w} s={s}", atol=atol)
+    # a clipped last frame shorter than num_fft makes the reference's scatter raise ValueError (:288)
+    bad = O.synth_clip(60, 16300, 16000)
+    with pytest.raises(ValueError):
+        O.chromagram(bad, 16000, 800, 200)
+    with pytest.raises(ValueError):
+        P.ShortTermFeatures.chromagram(bad, 16000, 800, 200)
+
+
 # ------------------------------------------------------------------ full-size properties (BASELINE configs[1])
 def test_full_size_properties(P):
     """1000 x 10 s @16 kHz: no oracle at this size -- use properties that do not depend on it."""
