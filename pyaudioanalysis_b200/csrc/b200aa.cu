@@ -232,7 +232,7 @@ static int build_blob(int fs, int K, std::vector<int> &blob, BlobLayout &bl, boo
     bl.chr_off = put_i(c_off);
     bl.chr_bin = put_i(c_bin);
     bl.chr_w = put_f(c_w);
-    {   // pair the longest filter with the shortest, 2nd longest with 2nd shortest, ...
+    {   // pair the longest filter with the shortest, 2nd longest with 2nd shortest, ... (balanced tap counts)
         std::vector<int> order(40);
         for (int i = 0; i < 40; ++i) order[i] = i;
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return m_count[a] < m_count[b]; });

@@ -8,6 +8,8 @@
 // Post-processing computes X[k] and X[Nc-k] from one (Z[k], Z[Nc-k]) pair, so only half of the
 // second-pass outputs travel through shared memory.
 #pragma once
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include "common.cuh"
 
@@ -73,8 +75,16 @@ __host__ __device__ constexpr int cx_modinv(int a, int m)
 // ----------------------------------------------------------------------------------------------
 // small forward DFTs on register arrays
 // ----------------------------------------------------------------------------------------------
+// Blackwell packed FP32: one FADD2 / FFMA2 instruction handles the (re, im) pair (sm_100 FP32x2 datapath)
+#ifndef B200AA_NO_F32X2
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 f2fma(float c, float2 a, float2 acc) { return __ffma2_rn(make_float2(c, c), a, acc); }
+#else
 __device__ __forceinline__ float2 f2add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 f2fma(float c, float2 a, float2 acc) { return make_float2(fmaf(c, a.x, acc.x), fmaf(c, a.y, acc.y)); }
+#endif
 
 template <int P>
 __device__ __forceinline__ void dft_small(float2 (&x)[P])
@@ -92,9 +102,13 @@ __device__ __forceinline__ void dft_small(float2 (&x)[P])
         // odd prime: y_k = x0 + sum_j [ (x_j + x_{P-j}) cos(2 pi j k / P) - i (x_j - x_{P-j}) sin(2 pi j k / P) ]
         constexpr Trig<P> T = make_trig<P>();
         constexpr int H = (P - 1) / 2;
-        float2 sp[H], dm[H], y[P];
+        float2 sp[H], dr[H], y[P];
 #pragma unroll
-        for (int j = 1; j <= H; ++j) { sp[j - 1] = f2add(x[j], x[P - j]); dm[j - 1] = f2sub(x[j], x[P - j]); }
+        for (int j = 1; j <= H; ++j) {
+            sp[j - 1] = f2add(x[j], x[P - j]);
+            // -i (x_j - x_{P-j}) = (dy, -dx): kept rotated so the odd part is a plain packed accumulate
+            dr[j - 1] = make_float2(x[j].y - x[P - j].y, x[P - j].x - x[j].x);
+        }
         y[0] = x[0];
 #pragma unroll
         for (int j = 0; j < H; ++j) y[0] = f2add(y[0], sp[j]);
@@ -103,14 +117,12 @@ __device__ __forceinline__ void dft_small(float2 (&x)[P])
             float2 re = x[0], im = make_float2(0.f, 0.f);
 #pragma unroll
             for (int j = 1; j <= H; ++j) {
-                const float c = T.c[(j * k) % P], s = T.s[(j * k) % P];
-                re.x = fmaf(c, sp[j - 1].x, re.x);
-                re.y = fmaf(c, sp[j - 1].y, re.y);
-                im.x = fmaf(s, dm[j - 1].x, im.x);
-                im.y = fmaf(s, dm[j - 1].y, im.y);
+                const float c = T.c[(j * k) % P], sn = T.s[(j * k) % P];
+                re = f2fma(c, sp[j - 1], re);
+                im = f2fma(sn, dr[j - 1], im);
             }
-            y[k] = make_float2(re.x + im.y, re.y - im.x);
-            y[P - k] = make_float2(re.x - im.y, re.y + im.x);
+            y[k] = f2add(re, im);
+            y[P - k] = f2sub(re, im);
         }
 #pragma unroll
         for (int k = 0; k < P; ++k) x[k] = y[k];
@@ -158,6 +170,7 @@ __device__ __forceinline__ void fft_r(float2 (&v)[R]) { fft_pfa<RFactors<R>::A, 
 // ----------------------------------------------------------------------------------------------
 // ---- cheap math: MUFU-based reciprocal / rsqrt / log2 (2 ulp); the parity tolerance is 1e-4
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
+// rsqrtf() is the MUFU.RSQ approximation; __frsqrt_rn() is the correctly rounded (slow) one -- measured 12 % slower
 __device__ __forceinline__ float fsqrt_pos(float x) { return x * rsqrtf(fmaxf(x, 1e-36f)); }   // 0 -> 0
 __device__ __forceinline__ float flog2(float x) { return __log2f(x); }
 
@@ -240,10 +253,12 @@ __device__ __forceinline__ DenseLane dense_lane_init(int lane)
 
 template <int K>
 __device__ __forceinline__ void spectral_features_k(const float *X, const float *Xp, float sxp, const float *chroma_raw,
-                                                    const DenseLane &dl, float *parts, float *fv, int lane, float *sx_out)
+                                                    const int *dlp, float *parts, float *fv, int lane, float *sx_out)
 {
     constexpr int C = DenseShape<K>::C;
     const int k0 = lane * C;
+    const int4 dlv = *reinterpret_cast<const int4 *>(dlp);        // {split, ps, pe, -}
+    DenseLane dl; dl.split = dlv.x; dl.ps = dlv.y; dl.pe = dlv.z;
     float x[C];
 #pragma unroll
     for (int i = 0; i < C; ++i) x[i] = X[k0 + i];
@@ -290,7 +305,9 @@ __device__ __forceinline__ void spectral_features_k(const float *X, const float 
     // ---- spectral entropy: lanes 0..9 add up the parts of their block (parts are in bin order)
     __syncwarp();
     float e = 0.f;
-    for (int q = dl.ps; q < dl.pe; ++q) e += parts[q];
+    constexpr int MAXP = 2 * (DenseShape<K>::Lb / C + 2);
+#pragma unroll
+    for (int q = 0; q < MAXP; ++q) e += (dl.ps + q < dl.pe) ? parts[dl.ps + q] : 0.f;
     float ent = 0.f;
     if (lane < 10) {
         const float sj = fdiv(e, sxx + B200AA_EPS);
@@ -503,24 +520,34 @@ struct FastShape {
     static constexpr int NT = 32 * G;            // threads per CTA
 };
 
+// fixed-size part of the CTA's shared memory (compile-time offsets)
 template <int R, int G>
-inline size_t fast_smem_bytes(int step, int blob_words)
+struct alignas(16) FastFixed {
+    using S = FastShape<R, G>;
+    float2 E[G * R * S::ES];              // transpose buffer [G][R][ES]; the |X| rows alias it
+    float2 tw[R * R];                     // W_Nc^(k1 n2)  [k1][n2]
+    float2 twp[(S::Nc / 2 + 2) & ~1];     // W_N^k
+    alignas(16) float Xprev[S::Kp];       // |X| of the previous frame
+    float fvrows[(G + 1) * kFvStride];    // feature rows (+ previous frame)
+    float mscr[G * B200AA_N_MEL];         // log-mel energies
+    float chr[G * 12];                    // raw chroma sums
+    float rowsum[G + 4];
+    float parts[G * 64];                  // entropy parts per warp
+    alignas(16) int dlane[32 * 4];        // per-lane constants of the dense pass
+    unsigned int next_item;
+};
+
+template <int R, int G>
+inline size_t fast_fixed_bytes() { return sizeof(FastFixed<R, G>); }
+template <int R, int G>
+inline size_t fast_smem_bytes(int step, int blob_words, bool runs)
 {
     using S = FastShape<R, G>;
     const size_t span_max = size_t(G - 1) * step + S::N;
-    auto up = [](size_t b) { return (b + 15) & ~size_t(15); };
-    size_t b = 0;
-    b += up(sizeof(float2) * G * R * S::ES);          // transpose buffer (the |X| rows alias it)
-    b += up(sizeof(float2) * G * S::ZS);              // published second-pass outputs
-    b += up(sizeof(float2) * R * R) + up(sizeof(float2) * (S::Nc / 2 + 1));
-    b += up(sizeof(float) * (span_max + 4));               // sample span
-    b += up(sizeof(float) * S::Kp);                        // |X| of the previous frame
-    b += up(sizeof(float) * (G + 1) * kFvStride);
-    b += up(sizeof(float) * G * B200AA_N_MEL) + up(sizeof(float) * G * 12) + up(sizeof(float) * (G + 1));
-    b += up(sizeof(float) * G * 64);
-    b += 2 * up(sizeof(float) * (span_max / 8 + 1));       // run partials
-    b += up(sizeof(int) * blob_words);
-    return b;
+    const size_t nrun = (span_max / 8 + 4) & ~size_t(3);
+    const bool zs_alias = runs && size_t(G) * step >= 2 * size_t(G) * S::ZS;   // see the kernel
+    return fast_fixed_bytes<R, G>() + sizeof(int) * ((blob_words + 3) & ~3) + 2 * sizeof(float) * nrun +
+           sizeof(float) * (span_max + 8) + (zs_alias ? 0 : sizeof(float2) * G * S::ZS);
 }
 
 template <int R, int G, bool STEP_EVEN, bool RUNS, int MODE>
@@ -531,24 +558,24 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
     constexpr int Nc = S::Nc, N = S::N, K = S::K, Kp = S::Kp, ES = S::ES, H = S::H, ZS = S::ZS, NT = S::NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int step = p.step;
-    const int span_max = (G - 1) * step + N;
-    // carve shared memory; every array starts on a 16-byte boundary (float4 / float2 accesses)
-    unsigned char *sp_ = smem_raw;
-    auto carve = [&](size_t bytes) { unsigned char *q = sp_; sp_ += (bytes + 15) & ~size_t(15); return q; };
-    float2 *E = reinterpret_cast<float2 *>(carve(sizeof(float2) * G * R * ES));         // [G][R][ES]
-    float2 *Zs = reinterpret_cast<float2 *>(carve(sizeof(float2) * G * ZS));            // [G][ZS]
-    float2 *s_tw = reinterpret_cast<float2 *>(carve(sizeof(float2) * R * R));           // [R][R]
-    float2 *s_twp = reinterpret_cast<float2 *>(carve(sizeof(float2) * (Nc / 2 + 1)));   // [Nc/2+1]
-    float *sS = reinterpret_cast<float *>(carve(sizeof(float) * (span_max + 4)));       // sample span
-    float *Xprev = reinterpret_cast<float *>(carve(sizeof(float) * Kp));                // |X| of the previous frame
-    float *fvrows = reinterpret_cast<float *>(carve(sizeof(float) * (G + 1) * kFvStride));
-    float *mscr = reinterpret_cast<float *>(carve(sizeof(float) * G * B200AA_N_MEL));   // [G][40] log-mel energies
-    float *chr = reinterpret_cast<float *>(carve(sizeof(float) * G * 12));              // [G][12] raw chroma sums
-    float *rowsum = reinterpret_cast<float *>(carve(sizeof(float) * (G + 1)));
-    float *parts = reinterpret_cast<float *>(carve(sizeof(float) * G * 64));        // entropy parts per warp
-    float *runE = reinterpret_cast<float *>(carve(sizeof(float) * (span_max / 8 + 1)));  // run partials (RUNS only)
-    int *runF = reinterpret_cast<int *>(carve(sizeof(int) * (span_max / 8 + 1)));
-    int *blob_s = reinterpret_cast<int *>(carve(sizeof(int) * p.bl.words));
+    // shared-memory layout: all fixed-size arrays sit at compile-time offsets (no address arithmetic to keep
+    // live in registers); the three arrays whose size depends on the hop come last
+    using Fixed = FastFixed<R, G>;
+    Fixed &sm = *reinterpret_cast<Fixed *>(smem_raw);
+    float2 *const E = sm.E, *const s_tw = sm.tw, *const s_twp = sm.twp;
+    float *const Xprev = sm.Xprev, *const fvrows = sm.fvrows, *const mscr = sm.mscr, *const chr = sm.chr;
+    float *const rowsum = sm.rowsum, *const parts = sm.parts;
+    int *const blob_s = reinterpret_cast<int *>(smem_raw + sizeof(Fixed));
+    const int blob_pad = (p.bl.words + 3) & ~3;
+    const int nrun = ((G - 1) * step + N) / 8 + 4 & ~3;
+    float *const runE = reinterpret_cast<float *>(blob_s + blob_pad);                 // run partials (RUNS only)
+    int *const runF = reinterpret_cast<int *>(runE + nrun);
+    float *const sS = reinterpret_cast<float *>(runF + nrun);                         // sample span
+    // published second-pass outputs [G][ZS]: with run partials the samples of the G frames are dead once
+    // pass 1 has read them (only the tail that the next step reuses must survive), so Zs lives on top of them
+    const bool zs_alias = RUNS && G * step >= 2 * G * ZS;
+    float2 *const Zs = zs_alias ? reinterpret_cast<float2 *>(sS)
+                                : reinterpret_cast<float2 *>(sS + (((G - 1) * step + N + 8) & ~3));
     float *Xrows = reinterpret_cast<float *>(E);                             // rows f -> Xrows + f*Kp (aliases E)
     static_assert(size_t(G) * Kp * sizeof(float) <= size_t(G) * R * ES * sizeof(float2), "alias");
     static_assert((G & (G - 1)) == 0 && G * 26 <= NT, "tile mapping");
@@ -559,15 +586,17 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
     for (int i = tid; i < Nc / 2 + 1; i += NT) s_twp[i] = g_twp[i];
     __syncthreads();
     const SmallTables tb = bind_tables(blob_s, p.bl);
-    const DenseLane dl = dense_lane_init<K>(lane);
+    if (tid < 32) {
+        const DenseLane d0_ = dense_lane_init<K>(tid);
+        sm.dlane[tid * 4 + 0] = d0_.split; sm.dlane[tid * 4 + 1] = d0_.ps; sm.dlane[tid * 4 + 2] = d0_.pe;
+    }
     for (int i = tid; i < Kp; i += NT) Xprev[i] = 0.f;
     const bool fft_thread = tid < S::FftThreads;
     const int ff = tid / R, fj = tid - ff * R;          // frame slot / index within the frame's R threads
 
     // work items are handed out dynamically (one atomic per item) so the tail of the launch is one item long
-    __shared__ unsigned int s_next_item;
     for (int64_t item = blockIdx.x; item < p.n_items;) {
-        if (tid == 0) s_next_item = atomicAdd(work_counter, 1u) + gridDim.x;
+        if (tid == 0) sm.next_item = atomicAdd(work_counter, 1u) + gridDim.x;
         do {
         const int64_t b = item / p.segs_per_clip, seg = item % p.segs_per_clip;
         const int64_t len = p.len ? p.len[b] : p.n_samples;
@@ -630,9 +659,10 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
             __syncthreads();
 
             // ---- pass 1: thread (frame ff, column n2 = fj): FFT over n1 of z[R*n1 + n2], twiddle, transpose
+            float d0 = 0.f;                 // first sample of the frame (kept for the DC bin)
             if (fft_thread && ff < ng) {
                 const float *fr = sS + ff * step;
-                const float d0 = fr[0];
+                d0 = fr[0];
                 float2 v[R];
 #pragma unroll
                 for (int n1 = 0; n1 < R; ++n1) {
@@ -682,7 +712,6 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
                     const int k = fj + R * k2;
                     if (k2 == 0 && fj == 0) {
                         // DC: a * sum(d - d0) + N * (a*d0 + bp)
-                        const float d0 = sS[ff * step];
                         Xf[0] = fabsf(fmaf(nm.a, v[0].x + v[0].y, float(N) * fmaf(nm.a, d0, nm.bp))) / float(K);
                     } else {
                         pair(k, v[k2], true);
@@ -748,7 +777,7 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
                     Xp = X;
                     sxp = row_sum_k<K>(X, lane);
                 }
-                spectral_features_k<K>(X, Xp, sxp, chr + f * 12, dl, parts + warp * 64, fv, lane, rowsum + f + 1);
+                spectral_features_k<K>(X, Xp, sxp, chr + f * 12, sm.dlane + lane * 4, parts + warp * 64, fv, lane, rowsum + f + 1);
             }
             __syncthreads();
             // ---- store the [n_out x 8] tile: 8 consecutive threads -> 8 consecutive frames of one feature row
@@ -773,7 +802,7 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
         }
         } while (0);
         __syncthreads();
-        item = s_next_item;
+        item = sm.next_item;
         __syncthreads();
     }
 }
@@ -821,7 +850,7 @@ template <int R, int G, bool EVEN, bool RUNS, int MODE>
 inline int fast_launch_t(const FastTables &ft, StParams p, int sm_count, int64_t T, cudaStream_t st)
 {
     constexpr int NT = 32 * G;
-    const size_t smem = fast_smem_bytes<R, G>(p.step, p.bl.words);
+    const size_t smem = fast_smem_bytes<R, G>(p.step, p.bl.words, RUNS);
     if (smem > 110u * 1024u) return B200AA_ERR_UNSUPPORTED;      // very large hop: leave it to the generic kernel
     auto kern = st_fast_kernel<R, G, EVEN, RUNS, MODE>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200AA_ERR_CUDA;
@@ -838,6 +867,9 @@ inline int fast_launch_t(const FastTables &ft, StParams p, int sm_count, int64_t
     p.segs_per_clip = (T + seg - 1) / seg;
     p.n_items = p.segs_per_clip * p.n_clips;
     const int64_t grid = p.n_items < slots ? p.n_items : slots;
+    if (getenv("B200AA_DEBUG"))
+        fprintf(stderr, "[b200aa] fast kernel R=%d G=%d runs=%d mode=%d: smem %zu B, %d CTAs/SM, grid %lld, %lld items of %lld frames\n",
+                R, G, int(RUNS), MODE, smem, occ, (long long)grid, (long long)p.n_items, (long long)seg);
     unsigned int *ctr = ft.d_counters + (ft.next_counter++ % 64u);
     if (cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st) != cudaSuccess) return B200AA_ERR_CUDA;
     kern<<<(unsigned)grid, NT, smem, st>>>(p, ft.d_tw, ft.d_twp, ctr);
