@@ -171,8 +171,23 @@ __device__ __forceinline__ void fft_r(float2 (&v)[R]) { fft_pfa<RFactors<R>::A, 
 // ---- cheap math: MUFU-based reciprocal / rsqrt / log2 (2 ulp); the parity tolerance is 1e-4
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
 // rsqrtf() is the MUFU.RSQ approximation; __frsqrt_rn() is the correctly rounded (slow) one -- measured 12 % slower
+#ifndef B200AA_NO_FTZ_MUFU
+__device__ __forceinline__ float fsqrt_pos(float x)      // bare MUFU.RSQ (flush-to-zero form: no denormal fix-up code)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(x, 1e-36f)));
+    return x * r;
+}
+__device__ __forceinline__ float flog2(float x)
+{
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+#else
 __device__ __forceinline__ float fsqrt_pos(float x) { return x * rsqrtf(fmaxf(x, 1e-36f)); }   // 0 -> 0
 __device__ __forceinline__ float flog2(float x) { return __log2f(x); }
+#endif
 
 // two sums with 5 exchanges + 2 broadcasts (instead of 10 exchanges)
 __device__ __forceinline__ void warp_sum2(float &a, float &b, int lane)
@@ -203,6 +218,30 @@ __device__ __forceinline__ float warp_sum4_grouped(float a, float b, float c, fl
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) k += __shfl_xor_sync(0xffffffffu, k, o);
     return k;
+}
+
+// the same folded DCT for one frame by one warp (lanes 0..25), used when the features run warp-per-frame
+__device__ __forceinline__ void warp_dct(const float *m, const SmallTables &tb, float *fvrow, int lane)
+{
+    const int c = lane >> 1, h = lane & 1;
+    float acc = 0.f;
+    const bool act = lane < 26;
+    if (act) {
+        const float kap = m[0];
+        const float *row = tb.dct + c * 41;
+        const float sgn = (c & 1) ? -1.f : 1.f;
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+            const int n = 10 * h + j;
+            const float a = m[n] - kap, b = m[39 - n] - kap;
+            acc = fmaf(row[n], fmaf(sgn, b, a), acc);
+        }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (act && h == 0) {
+        if (c == 0) acc = fmaf(6.324555320336759f, m[0], acc);
+        fvrow[8 + c] = acc;
+    }
 }
 
 template <int K>
@@ -253,7 +292,7 @@ __device__ __forceinline__ DenseLane dense_lane_init(int lane)
 
 template <int K>
 __device__ __forceinline__ void spectral_features_k(const float *X, const float *Xp, float sxp, const float *chroma_raw,
-                                                    const int *dlp, float *parts, float *fv, int lane, float *sx_out)
+                                                    const int *dlp, float *parts, float *fv, int lane, float *xsave)
 {
     constexpr int C = DenseShape<K>::C;
     const int k0 = lane * C;
@@ -262,6 +301,10 @@ __device__ __forceinline__ void spectral_features_k(const float *X, const float 
     float x[C];
 #pragma unroll
     for (int i = 0; i < C; ++i) x[i] = X[k0 + i];
+    if (xsave) {                                     // last frame of the step: keep |X| for the next step's flux
+#pragma unroll
+        for (int i = 0; i < C; ++i) xsave[k0 + i] = x[i];
+    }
     // ---- sums: sum X, sum (k+1) X, sum X^2 split at the entropy-block boundary inside the chunk
     float sx = 0.f, s1 = 0.f, plo = 0.f, phi = 0.f;
 #pragma unroll
@@ -325,7 +368,7 @@ __device__ __forceinline__ void spectral_features_k(const float *X, const float 
         fv[3] = cen;
         fv[4] = sx > 0.f ? fsqrt_pos(fdiv(q4, sx)) : 0.f;
         fv[33] = fsqrt_pos(var);
-        *sx_out = sx;
+        fv[34] = sx;                                 // kept with the row: the next frame's flux needs it
     }
     if (lane == 8) fv[6] = q4;
     if (lane == 16) fv[7] = q4 >= float(K) ? 0.f : q4 * invK;
@@ -350,6 +393,7 @@ __device__ __forceinline__ void flat_mel_chroma(const float *Xrows, int Kp, int 
                 const int s0 = tb.mel_start[i], cnt = tb.mel_count[i], off = tb.mel_off[i];
                 float acc = 0.f;
                 for (int t = 0; t < cnt; ++t) acc = fmaf(X[s0 + t], tb.mel_w[off + t], acc);
+
                 ms[f * B200AA_N_MEL + i] = 0.30102999566398120f * flog2(acc + B200AA_EPS);   // log10
             }
         }
@@ -374,7 +418,7 @@ __device__ __forceinline__ void flat_mel_chroma(const float *Xrows, int Kp, int 
 //   c >= 1 because those rows are orthogonal to constants; row 0 adds it back): keeps the float32 sum
 //   free of the large common offset of the log-mel values.
 template <int G>
-__device__ __forceinline__ void flat_dct(const float *ms, int ng, const SmallTables &tb, float *fvrows, int tid)
+__device__ __forceinline__ void flat_dct(const float *ms, int ng, const SmallTables &tb, float *fvrows, int fbase, int tid)
 {
     const int f = tid / 26, r = tid - f * 26;
     const int c = r >> 1, h = r & 1;
@@ -395,7 +439,9 @@ __device__ __forceinline__ void flat_dct(const float *ms, int ng, const SmallTab
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     if (act && h == 0) {
         if (c == 0) acc = fmaf(6.324555320336759f, ms[f * B200AA_N_MEL], acc);    // sqrt(1/40) * 40 * k
-        fvrows[size_t(f + 1) * kFvStride + 8 + c] = acc;
+        int r = fbase + 1 + f;
+        if (r > G) r -= G + 1;
+        fvrows[r * kFvStride + 8 + c] = acc;
     }
 }
 
@@ -527,11 +573,10 @@ struct alignas(16) FastFixed {
     float2 E[G * R * S::ES];              // transpose buffer [G][R][ES]; the |X| rows alias it
     float2 tw[R * R];                     // W_Nc^(k1 n2)  [k1][n2]
     float2 twp[(S::Nc / 2 + 2) & ~1];     // W_N^k
-    alignas(16) float Xprev[S::Kp];       // |X| of the previous frame
-    float fvrows[(G + 1) * kFvStride];    // feature rows (+ previous frame)
+    alignas(16) float Xprev[2 * S::Kp];   // |X| of the previous step's last frame (double-buffered)
+    float fvrows[(G + 1) * kFvStride];    // ring of feature rows: 34 features + the row's sum(X) in slot 34
     float mscr[G * B200AA_N_MEL];         // log-mel energies
     float chr[G * 12];                    // raw chroma sums
-    float rowsum[G + 4];
     float parts[G * 64];                  // entropy parts per warp
     alignas(16) int dlane[32 * 4];        // per-lane constants of the dense pass
     unsigned int next_item;
@@ -564,7 +609,7 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
     Fixed &sm = *reinterpret_cast<Fixed *>(smem_raw);
     float2 *const E = sm.E, *const s_tw = sm.tw, *const s_twp = sm.twp;
     float *const Xprev = sm.Xprev, *const fvrows = sm.fvrows, *const mscr = sm.mscr, *const chr = sm.chr;
-    float *const rowsum = sm.rowsum, *const parts = sm.parts;
+    float *const parts = sm.parts;
     int *const blob_s = reinterpret_cast<int *>(smem_raw + sizeof(Fixed));
     const int blob_pad = (p.bl.words + 3) & ~3;
     const int nrun = ((G - 1) * step + N) / 8 + 4 & ~3;
@@ -590,7 +635,7 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
         const DenseLane d0_ = dense_lane_init<K>(tid);
         sm.dlane[tid * 4 + 0] = d0_.split; sm.dlane[tid * 4 + 1] = d0_.ps; sm.dlane[tid * 4 + 2] = d0_.pe;
     }
-    for (int i = tid; i < Kp; i += NT) Xprev[i] = 0.f;
+    for (int i = tid; i < 2 * Kp; i += NT) Xprev[i] = 0.f;
     const bool fft_thread = tid < S::FftThreads;
     const int ff = tid / R, fj = tid - ff * R;          // frame slot / index within the frame's R threads
 
@@ -601,12 +646,13 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
         const int64_t b = item / p.segs_per_clip, seg = item % p.segs_per_clip;
         const int64_t len = p.len ? p.len[b] : p.n_samples;
         // features: frames of the clip; spectrogram / chromagram: the rows of this launch (rows >= n_valid are zero)
-        const int64_t T = MODE == kModeFeatures ? (len < N ? 0 : (len - N) / step + 1) : p.rows_launch;
-        const int64_t n_valid = MODE == kModeFeatures ? T : p.rows_valid;
+        typedef int fidx_t;          // frame / row indices inside a clip fit 32 bits (checked on the host)
+        const fidx_t T = fidx_t(MODE == kModeFeatures ? (len < N ? 0 : (len - N) / step + 1) : p.rows_launch);
+        const fidx_t n_valid = MODE == kModeFeatures ? T : fidx_t(p.rows_valid);
         const int64_t origin = MODE == kModeFeatures ? 0 : p.origin;
-        const int64_t t0 = seg * p.seg_len;
+        const fidx_t t0 = fidx_t(seg * p.seg_len);
         if (t0 >= T) break;
-        const int64_t t1 = (t0 + p.seg_len) < T ? (t0 + p.seg_len) : T;
+        const fidx_t t1 = (t0 + fidx_t(p.seg_len)) < T ? (t0 + fidx_t(p.seg_len)) : T;
         const b200aa_clip_norm nm = p.norm[b];
         const char *clip = reinterpret_cast<const char *>(p.sig) +
                            size_t(b) * p.clip_stride * (p.dtype == B200AA_DTYPE_I16 ? 2 : 4);
@@ -615,7 +661,9 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
         // 16-byte loads need the clip base and the step's first sample aligned (8 samples of int16)
         const bool vec_ok = (reinterpret_cast<uintptr_t>(clip) & 15) == 0 && (p.dtype == B200AA_DTYPE_I16 || (step % 4 == 0));
 
-        for (int64_t g0 = t0 - halo; g0 < t1; g0 += G) {
+        int fbase = 0;        // ring row that holds the previous frame's features
+        int xsel = 0;         // which half of Xprev holds the previous step's last |X|
+        for (fidx_t g0 = t0 - halo; g0 < t1; g0 += G) {
             const int nrow = int((t1 - g0) < G ? (t1 - g0) : G);          // rows / frames of this step
             // frames that exist (spectrogram / chromagram allocate more rows than their loops fill)
             const int ng = int((n_valid - g0) < nrow ? ((n_valid - g0) > 0 ? (n_valid - g0) : 0) : nrow);
@@ -630,7 +678,7 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
             }
             // ---- stage the sample span of this step as float (x - m)
             const int span = (ng - 1) * step + N;
-            const int64_t sbase = origin + g0 * step;
+            const int64_t sbase = origin + int64_t(g0) * step;
             if (RUNS) {
                 // samples shared with the previous step are already converted: move them to the front
                 int keep = 0;
@@ -754,16 +802,30 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
                 continue;
             }
             // ---- flat phase: mel + log10 / raw chroma over all 8 frames, then DCT rows; dense features per warp
+#ifndef B200AA_E2
             flat_mel_chroma<G>(Xrows, Kp, ng, tb, blob_s + p.bl.mel_pairs, mscr, chr, tid);
             __syncthreads();
-            flat_dct<G>(mscr, ng, tb, fvrows, tid);
+            flat_dct<G>(mscr, ng, tb, fvrows, fbase, tid);
+#endif
             for (int f = warp; f < ng; f += G) {
-                const int64_t fr = g0 + f;
+#ifdef B200AA_E2
+                {   // warp-per-frame variant: no CTA barrier between mel / chroma and their consumers
+                    int r2 = fbase + 1 + f;
+                    if (r2 > G) r2 -= G + 1;
+                    flat_mel_chroma<1>(Xrows + size_t(f) * Kp, Kp, 1, tb, blob_s + p.bl.mel_pairs, mscr + f * B200AA_N_MEL,
+                                       chr + f * 12, lane);
+                    __syncwarp();
+                    warp_dct(mscr + f * B200AA_N_MEL, tb, fvrows + r2 * kFvStride, lane);
+                }
+#endif
+                const fidx_t fr = g0 + f;
                 const float *X = Xrows + size_t(f) * Kp;
                 const bool has_prev = (fr > 0) && !(f == 0 && g0 == t0 - halo);
                 float sxp;
                 const float *Xp;
-                float *fv = fvrows + size_t(f + 1) * kFvStride;
+                int rr = fbase + 1 + f;
+                if (rr > G) rr -= G + 1;
+                float *fv = fvrows + rr * kFvStride;
                 const float *frs = sS + f * step;
                 if (RUNS) time_features_runs<N>(runE + (f * step) / 8, runF + (f * step) / 8, fv, lane);
                 else time_features([&](int n) { return frs[n]; }, N, nm, fv, lane);
@@ -771,34 +833,39 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
                     Xp = Xrows + size_t(f - 1) * Kp;
                     sxp = row_sum_k<K>(Xp, lane);      // the neighbour's warp produces its own copy concurrently
                 } else if (has_prev) {
-                    Xp = Xprev;
-                    sxp = rowsum[0];
+                    Xp = Xprev + xsel * Kp;
+                    sxp = fvrows[fbase * kFvStride + 34];
                 } else {
                     Xp = X;
                     sxp = row_sum_k<K>(X, lane);
                 }
-                spectral_features_k<K>(X, Xp, sxp, chr + f * 12, sm.dlane + lane * 4, parts + warp * 64, fv, lane, rowsum + f + 1);
+                spectral_features_k<K>(X, Xp, sxp, chr + f * 12, sm.dlane + lane * 4, parts + warp * 64, fv, lane,
+                                       f == ng - 1 ? Xprev + (xsel ^ 1) * Kp : nullptr);
             }
             __syncthreads();
             // ---- store the [n_out x 8] tile: 8 consecutive threads -> 8 consecutive frames of one feature row
+            float *const out_b = p.out + size_t(b) * p.n_out * p.t_stride + g0;
             for (int e = tid; e < p.n_out * G; e += NT) {
                 const int f = e / G, c = e % G;
-                const int64_t fr = g0 + c;
+                const fidx_t fr = g0 + c;
                 if (c >= ng || fr < t0) continue;
+                int r1 = fbase + 1 + c;
+                if (r1 > G) r1 -= G + 1;
+                int r0 = fbase + c;
+                if (r0 > G) r0 -= G + 1;
                 float val;
-                if (f < B200AA_N_BASE) val = fvrows[size_t(c + 1) * kFvStride + f];
+                if (f < B200AA_N_BASE) val = fvrows[r1 * kFvStride + f];
                 else {
                     const int fb = f - B200AA_N_BASE;
-                    val = fr == 0 ? 0.f : fvrows[size_t(c + 1) * kFvStride + fb] - fvrows[size_t(c) * kFvStride + fb];
+                    val = fr == 0 ? 0.f : fvrows[r1 * kFvStride + fb] - fvrows[r0 * kFvStride + fb];
                 }
-                p.out[(size_t(b) * p.n_out + f) * p.t_stride + fr] = val;
+                out_b[size_t(f) * p.t_stride + c] = val;
             }
-            // ---- carry the last frame of the step
-            for (int k = tid; k < K; k += NT) Xprev[k] = Xrows[size_t(ng - 1) * Kp + k];   // padding of Xprev stays 0
-            __syncthreads();
-            if (tid < kFvStride) fvrows[tid] = fvrows[size_t(ng) * kFvStride + tid];
-            if (tid == 0) rowsum[0] = rowsum[ng];
-            __syncthreads();
+            // the last frame of this step becomes "previous" for the next one: advance the ring / flip the buffer
+            // (no copies, no barrier: the next step's writers of these arrays run several barriers later)
+            fbase += ng;
+            if (fbase > G) fbase -= G + 1;
+            xsel ^= 1;
         }
         } while (0);
         __syncthreads();
