@@ -220,30 +220,6 @@ __device__ __forceinline__ float warp_sum4_grouped(float a, float b, float c, fl
     return k;
 }
 
-// the same folded DCT for one frame by one warp (lanes 0..25), used when the features run warp-per-frame
-__device__ __forceinline__ void warp_dct(const float *m, const SmallTables &tb, float *fvrow, int lane)
-{
-    const int c = lane >> 1, h = lane & 1;
-    float acc = 0.f;
-    const bool act = lane < 26;
-    if (act) {
-        const float kap = m[0];
-        const float *row = tb.dct + c * 41;
-        const float sgn = (c & 1) ? -1.f : 1.f;
-#pragma unroll
-        for (int j = 0; j < 10; ++j) {
-            const int n = 10 * h + j;
-            const float a = m[n] - kap, b = m[39 - n] - kap;
-            acc = fmaf(row[n], fmaf(sgn, b, a), acc);
-        }
-    }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    if (act && h == 0) {
-        if (c == 0) acc = fmaf(6.324555320336759f, m[0], acc);
-        fvrow[8 + c] = acc;
-    }
-}
-
 template <int K>
 struct DenseShape {
     static constexpr int C = ((K + 31) / 32) | 1;   // bins per lane (odd => conflict-free chunk loads)
@@ -507,6 +483,64 @@ __device__ __forceinline__ void stage_run(const void *clip, int dtype, bool vec_
     *runF = fli | (link << 8);
 }
 
+// ----------------------------------------------------------------------------------------------
+// TMA (1-D bulk async copy) + mbarrier: the raw int16 samples of the NEXT CTA step are fetched from
+// HBM into shared memory by the copy engine while this step's FFT / features run
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar)
+{
+    // order the CTA's earlier generic-proxy reads of the buffer before the async-proxy write
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+
+// stage_run() with the 8 int16 samples (and their predecessor) already in shared memory
+__device__ __forceinline__ void stage_run_smem(const short *raw8, bool has_pred, const b200aa_clip_norm &nm, float *dst, float *runE,
+                                               int *runF)
+{
+    const int4 q = *reinterpret_cast<const int4 *>(raw8);
+    const int w4[4] = {q.x, q.y, q.z, q.w};
+    float d[8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        d[2 * u] = float((short)(w4[u] & 0xffff)) - nm.m;
+        d[2 * u + 1] = float(w4[u] >> 16) - nm.m;
+    }
+    float e = 0.f, fl = 0.f, s[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const float y = fmaf(nm.a, d[u], nm.bp);
+        e = fmaf(y, y, e);
+        s[u] = sign_class(d[u], nm.lo, nm.hi);
+        if (u > 0) fl += fabsf(s[u] - s[u - 1]);
+    }
+    float linkf = 0.f;
+    if (has_pred) linkf = fabsf(s[0] - sign_class(float(raw8[-1]) - nm.m, nm.lo, nm.hi));
+    *reinterpret_cast<float4 *>(dst) = make_float4(d[0], d[1], d[2], d[3]);
+    *reinterpret_cast<float4 *>(dst + 4) = make_float4(d[4], d[5], d[6], d[7]);
+    *runE = e;
+    *runF = int(fl) | (int(linkf) << 8);
+}
+
 // zcr, energy, energy entropy of one frame from its runs (warp; lanes 0..9 own the 10 entropy blocks)
 template <int N>
 __device__ __forceinline__ void time_features_runs(const float *runE, const int *runF, float *fv, int lane)
@@ -580,6 +614,7 @@ struct alignas(16) FastFixed {
     float parts[G * 64];                  // entropy parts per warp
     alignas(16) int dlane[32 * 4];        // per-lane constants of the dense pass
     unsigned int next_item;
+    alignas(8) unsigned long long mbar;   // completion barrier of the TMA prefetch
 };
 
 template <int R, int G>
@@ -592,7 +627,8 @@ inline size_t fast_smem_bytes(int step, int blob_words, bool runs)
     const size_t nrun = (span_max / 8 + 4) & ~size_t(3);
     const bool zs_alias = runs && size_t(G) * step >= 2 * size_t(G) * S::ZS;   // see the kernel
     return fast_fixed_bytes<R, G>() + sizeof(int) * ((blob_words + 3) & ~3) + 2 * sizeof(float) * nrun +
-           sizeof(float) * (span_max + 8) + (zs_alias ? 0 : sizeof(float2) * G * S::ZS);
+           sizeof(float) * (span_max + 8) + (zs_alias ? 0 : sizeof(float2) * G * S::ZS) +
+           (runs ? sizeof(short) * (size_t(G) * step + 16) : 0);
 }
 
 template <int R, int G, bool STEP_EVEN, bool RUNS, int MODE>
@@ -621,6 +657,8 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
     const bool zs_alias = RUNS && G * step >= 2 * G * ZS;
     float2 *const Zs = zs_alias ? reinterpret_cast<float2 *>(sS)
                                 : reinterpret_cast<float2 *>(sS + (((G - 1) * step + N + 8) & ~3));
+    // raw int16 landing zone of the TMA prefetch (RUNS only): 8 predecessor samples + G*step new samples
+    short *const raw = reinterpret_cast<short *>(sS + (((G - 1) * step + N + 8) & ~3) + (zs_alias ? 0 : 2 * G * ZS));
     float *Xrows = reinterpret_cast<float *>(E);                             // rows f -> Xrows + f*Kp (aliases E)
     static_assert(size_t(G) * Kp * sizeof(float) <= size_t(G) * R * ES * sizeof(float2), "alias");
     static_assert((G & (G - 1)) == 0 && G * 26 <= NT, "tile mapping");
@@ -636,6 +674,9 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
         sm.dlane[tid * 4 + 0] = d0_.split; sm.dlane[tid * 4 + 1] = d0_.ps; sm.dlane[tid * 4 + 2] = d0_.pe;
     }
     for (int i = tid; i < 2 * Kp; i += NT) Xprev[i] = 0.f;
+    if (RUNS && tid == 0) mbar_init(&sm.mbar, 1);
+    unsigned tma_phase = 0;       // parity of the next completion to wait for
+    __syncthreads();
     const bool fft_thread = tid < S::FftThreads;
     const int ff = tid / R, fj = tid - ff * R;          // frame slot / index within the frame's R threads
 
@@ -662,6 +703,7 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
         const bool vec_ok = (reinterpret_cast<uintptr_t>(clip) & 15) == 0 && (p.dtype == B200AA_DTYPE_I16 || (step % 4 == 0));
 
         int fbase = 0;        // ring row that holds the previous frame's features
+        bool prefetched = false;   // this step's new samples were fetched by TMA during the previous step
         int xsel = 0;         // which half of Xprev holds the previous step's last |X|
         for (fidx_t g0 = t0 - halo; g0 < t1; g0 += G) {
             const int nrow = int((t1 - g0) < G ? (t1 - g0) : G);          // rows / frames of this step
@@ -699,12 +741,30 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
                         if (tid + u * NT < keep / 4) *reinterpret_cast<float4 *>(sS + 4 * (tid + u * NT)) = cv[u];
                     if (tid < keep / 8) { runE[tid] = ce[0]; runF[tid] = cf[0]; }
                 }
-                for (int r = keep / 8 + tid; r < span / 8; r += NT)
-                    stage_run(clip, p.dtype, vec_ok, sbase + 8 * r, nm, sS + 8 * r, runE + r, runF + r);
+                if (prefetched) {
+                    mbar_wait(&sm.mbar, tma_phase);
+                    tma_phase ^= 1u;
+                    for (int r = keep / 8 + tid; r < span / 8; r += NT)
+                        stage_run_smem(raw + 8 + 8 * (r - keep / 8), true, nm, sS + 8 * r, runE + r, runF + r);
+                } else {
+                    for (int r = keep / 8 + tid; r < span / 8; r += NT)
+                        stage_run(clip, p.dtype, vec_ok, sbase + 8 * r, nm, sS + 8 * r, runE + r, runF + r);
+                }
             } else {
                 for (int i = tid; i < span; i += NT) sS[i] = rd(sbase + i);
             }
             __syncthreads();
+            // ---- TMA: fetch the next step's new samples (same work item) while this step computes
+            prefetched = false;
+            if (RUNS && MODE == kModeFeatures && p.dtype == B200AA_DTYPE_I16 && vec_ok && step < N && g0 + G < t1) {
+                const fidx_t gn = g0 + G;
+                const int ngn = int((t1 - gn) < G ? (t1 - gn) : G);
+                const int keepn = N - step;
+                const int cnt = (ngn - 1) * step + N - keepn;                    // new samples of that step
+                const short *src = reinterpret_cast<const short *>(clip) + (origin + int64_t(gn) * step + keepn - 8);
+                if (tid == 0) tma_load_1d(raw, src, unsigned(cnt + 8) * 2u, &sm.mbar);
+                prefetched = true;
+            }
 
             // ---- pass 1: thread (frame ff, column n2 = fj): FFT over n1 of z[R*n1 + n2], twiddle, transpose
             float d0 = 0.f;                 // first sample of the frame (kept for the DC bin)
@@ -802,22 +862,10 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
                 continue;
             }
             // ---- flat phase: mel + log10 / raw chroma over all 8 frames, then DCT rows; dense features per warp
-#ifndef B200AA_E2
             flat_mel_chroma<G>(Xrows, Kp, ng, tb, blob_s + p.bl.mel_pairs, mscr, chr, tid);
             __syncthreads();
             flat_dct<G>(mscr, ng, tb, fvrows, fbase, tid);
-#endif
             for (int f = warp; f < ng; f += G) {
-#ifdef B200AA_E2
-                {   // warp-per-frame variant: no CTA barrier between mel / chroma and their consumers
-                    int r2 = fbase + 1 + f;
-                    if (r2 > G) r2 -= G + 1;
-                    flat_mel_chroma<1>(Xrows + size_t(f) * Kp, Kp, 1, tb, blob_s + p.bl.mel_pairs, mscr + f * B200AA_N_MEL,
-                                       chr + f * 12, lane);
-                    __syncwarp();
-                    warp_dct(mscr + f * B200AA_N_MEL, tb, fvrows + r2 * kFvStride, lane);
-                }
-#endif
                 const fidx_t fr = g0 + f;
                 const float *X = Xrows + size_t(f) * Kp;
                 const bool has_prev = (fr > 0) && !(f == 0 && g0 == t0 - halo);
