@@ -122,7 +122,7 @@ def hbm_peak():
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    cb, frames, dt = cpu_baseline(target_seconds=15.0)
+    cb, frames, dt = cpu_baseline(target_seconds=30.0)
     steps = max(1, args.steps)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "frames/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak",
@@ -294,7 +294,7 @@ def run_ours(args, rank, world, local_rank):
                          "note": "kernel is FP32-issue bound, not HBM bound (DESIGN.md): ~30 kFLOP per 1074 B frame"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches)}
     if world == 1 and not args.no_cpu:
-        line["cpu_baseline"], _, _ = cpu_baseline(target_seconds=15.0)
+        line["cpu_baseline"], _, _ = cpu_baseline(target_seconds=30.0)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
