@@ -368,6 +368,7 @@ __device__ __forceinline__ void flat_mel_chroma(const float *Xrows, int Kp, int 
                 const int i = pair_tab[2 * pr + h];
                 const int s0 = tb.mel_start[i], cnt = tb.mel_count[i], off = tb.mel_off[i];
                 float acc = 0.f;
+#pragma unroll 4
                 for (int t = 0; t < cnt; ++t) acc = fmaf(X[s0 + t], tb.mel_w[off + t], acc);
 
                 ms[f * B200AA_N_MEL + i] = 0.30102999566398120f * flog2(acc + B200AA_EPS);   // log10
