@@ -1,0 +1,142 @@
+// Small forward DFT codelets on register arrays (compile-time trigonometry, Blackwell FP32x2 butterflies).
+// Shared by the register-tiled kernel (fast_kernel.cuh) and the butterfly passes of the generic kernel.
+#pragma once
+#include "common.cuh"
+
+namespace b200aa {
+
+// ----------------------------------------------------------------------------------------------
+// compile-time trigonometry (exact argument reduction in turns, Taylor series in double)
+// ----------------------------------------------------------------------------------------------
+constexpr double kCxPi = 3.14159265358979323846264338327950288;
+
+__host__ __device__ constexpr double cx_sin_small(double x)   // |x| <= pi/2
+{
+    double x2 = x * x, term = x, sum = x;
+    for (int i = 1; i < 16; ++i) { term *= -x2 / double((2 * i) * (2 * i + 1)); sum += term; }
+    return sum;
+}
+__host__ __device__ constexpr double cx_cos_small(double x)
+{
+    double x2 = x * x, term = 1.0, sum = 1.0;
+    for (int i = 1; i < 16; ++i) { term *= -x2 / double((2 * i - 1) * (2 * i)); sum += term; }
+    return sum;
+}
+// cos / sin of 2*pi*p/q
+__host__ __device__ constexpr double cx_cos_turn(long p, long q)
+{
+    p %= q; if (p < 0) p += q;
+    if (2 * p > q) p = q - p;                 // cos(2 pi (1 - r)) = cos(2 pi r)
+    if (4 * p > q) return -cx_cos_small(2.0 * kCxPi * double(q - 2 * p) / double(2 * q));   // cos(pi - y) = -cos y
+    return cx_cos_small(2.0 * kCxPi * double(p) / double(q));
+}
+__host__ __device__ constexpr double cx_sin_turn(long p, long q)
+{
+    p %= q; if (p < 0) p += q;
+    double sign = 1.0;
+    if (2 * p > q) { p = q - p; sign = -1.0; }            // sin(2 pi (1 - r)) = -sin(2 pi r)
+    if (4 * p > q) return sign * cx_sin_small(2.0 * kCxPi * double(q - 2 * p) / double(2 * q));   // sin(pi - y) = sin y
+    return sign * cx_sin_small(2.0 * kCxPi * double(p) / double(q));
+}
+
+template <int P>
+struct Trig { float c[P], s[P]; };
+template <int P>
+__host__ __device__ constexpr Trig<P> make_trig()
+{
+    Trig<P> t{};
+    for (int j = 0; j < P; ++j) { t.c[j] = float(cx_cos_turn(j, P)); t.s[j] = float(cx_sin_turn(j, P)); }
+    return t;
+}
+__host__ __device__ constexpr int cx_modinv(int a, int m)
+{
+    a %= m;
+    for (int x = 1; x < m; ++x) if ((a * x) % m == 1) return x;
+    return 1;
+}
+
+// ----------------------------------------------------------------------------------------------
+// small forward DFTs on register arrays
+// ----------------------------------------------------------------------------------------------
+// Blackwell packed FP32: one FADD2 / FFMA2 instruction handles the (re, im) pair (sm_100 FP32x2 datapath)
+#ifndef B200AA_NO_F32X2
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 f2fma(float c, float2 a, float2 acc) { return __ffma2_rn(make_float2(c, c), a, acc); }
+#else
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 f2fma(float c, float2 a, float2 acc) { return make_float2(fmaf(c, a.x, acc.x), fmaf(c, a.y, acc.y)); }
+#endif
+
+template <int P>
+__device__ __forceinline__ void dft_small(float2 (&x)[P])
+{
+    if constexpr (P == 2) {
+        const float2 a = x[0], b = x[1];
+        x[0] = f2add(a, b); x[1] = f2sub(a, b);
+    } else if constexpr (P == 4) {
+        const float2 a = f2add(x[0], x[2]), b = f2sub(x[0], x[2]), c = f2add(x[1], x[3]), d = f2sub(x[1], x[3]);
+        x[0] = f2add(a, c);
+        x[2] = f2sub(a, c);
+        x[1] = make_float2(b.x + d.y, b.y - d.x);      // b - i d
+        x[3] = make_float2(b.x - d.y, b.y + d.x);      // b + i d
+    } else {
+        // odd prime: y_k = x0 + sum_j [ (x_j + x_{P-j}) cos(2 pi j k / P) - i (x_j - x_{P-j}) sin(2 pi j k / P) ]
+        constexpr Trig<P> T = make_trig<P>();
+        constexpr int H = (P - 1) / 2;
+        float2 sp[H], dr[H], y[P];
+#pragma unroll
+        for (int j = 1; j <= H; ++j) {
+            sp[j - 1] = f2add(x[j], x[P - j]);
+            // -i (x_j - x_{P-j}) = (dy, -dx): kept rotated so the odd part is a plain packed accumulate
+            dr[j - 1] = make_float2(x[j].y - x[P - j].y, x[P - j].x - x[j].x);
+        }
+        y[0] = x[0];
+#pragma unroll
+        for (int j = 0; j < H; ++j) y[0] = f2add(y[0], sp[j]);
+#pragma unroll
+        for (int k = 1; k <= H; ++k) {
+            float2 re = x[0], im = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 1; j <= H; ++j) {
+                const float c = T.c[(j * k) % P], sn = T.s[(j * k) % P];
+                re = f2fma(c, sp[j - 1], re);
+                im = f2fma(sn, dr[j - 1], im);
+            }
+            y[k] = f2add(re, im);
+            y[P - k] = f2sub(re, im);
+        }
+#pragma unroll
+        for (int k = 0; k < P; ++k) x[k] = y[k];
+    }
+}
+
+// prime-factor FFT of length RA*RB (coprime), natural order in, natural order out
+template <int RA, int RB>
+__device__ __forceinline__ void fft_pfa(float2 (&v)[RA * RB])
+{
+    constexpr int N = RA * RB;
+    float2 U[N];
+#pragma unroll
+    for (int a = 0; a < RA; ++a) {
+        float2 t[RB];
+#pragma unroll
+        for (int b = 0; b < RB; ++b) t[b] = v[(RB * a + RA * b) % N];
+        dft_small<RB>(t);
+#pragma unroll
+        for (int b = 0; b < RB; ++b) U[a * RB + b] = t[b];
+    }
+    constexpr int ca = RB * cx_modinv(RB, RA), cb = RA * cx_modinv(RA, RB);
+#pragma unroll
+    for (int kb = 0; kb < RB; ++kb) {
+        float2 t[RA];
+#pragma unroll
+        for (int a = 0; a < RA; ++a) t[a] = U[a * RB + kb];
+        dft_small<RA>(t);
+#pragma unroll
+        for (int ka = 0; ka < RA; ++ka) v[(ka * ca + kb * cb) % N] = t[ka];
+    }
+}
+
+}  // namespace b200aa

@@ -4,6 +4,7 @@
 // register-tiled kernels in fast_kernel.cuh take over for the window lengths they specialise.
 #pragma once
 #include "common.cuh"
+#include "dft_codelets.cuh"
 
 namespace b200aa {
 
@@ -17,6 +18,32 @@ inline size_t generic_smem_bytes(int G, int Nc, int Kp, int blob_words)
     b += size_t(G + 1) * sizeof(float);                      // row sums
     b += size_t(blob_words) * sizeof(int);
     return (b + 15) & ~size_t(15);
+}
+
+// One Stockham pass of radix R with one BUTTERFLY per thread (R = 2, 3, 4, 5, 7: register codelets of
+// dft_codelets.cuh); other radices use the one-output-per-thread form inside the kernel.
+template <int R>
+__device__ __forceinline__ void stockham_pass_bfly(const float2 *src, float2 *dst, int ng, int Nc, int Ns,
+                                                   const float2 *__restrict__ tw, int tid)
+{
+    const int nb = Nc / R, tstep = Nc / (Ns * R);
+    for (int e = tid; e < ng * nb; e += kThreads) {
+        const int f = e / nb, j = e - f * nb;
+        const int k = j % Ns;
+        const float2 *in = src + size_t(f) * Nc + j;
+        float2 v[R];
+        v[0] = in[0];
+        int idx = 0;
+#pragma unroll
+        for (int r = 1; r < R; ++r) {
+            idx += k * tstep;                      // (k * r * tstep) < Nc because k < Ns and r < R
+            v[r] = cmul(in[r * nb], __ldg(tw + idx));
+        }
+        dft_small<R>(v);
+        float2 *out = dst + size_t(f) * Nc + (j - k) * R + k;
+#pragma unroll
+        for (int q = 0; q < R; ++q) out[q * Ns] = v[q];
+    }
 }
 
 template <int MODE>
@@ -82,6 +109,12 @@ __global__ void __launch_bounds__(kThreads) st_generic_kernel(const StParams p)
             for (int ps = 0; ps < p.nrad; ++ps) {
                 const int R = p.radix[ps];
                 const int NsR = Ns * R, stride = Nc / R, tstep = Nc / NsR;
+                if (R == 4) stockham_pass_bfly<4>(src, dst, ng, Nc, Ns, p.tw, tid);
+                else if (R == 2) stockham_pass_bfly<2>(src, dst, ng, Nc, Ns, p.tw, tid);
+                else if (R == 3) stockham_pass_bfly<3>(src, dst, ng, Nc, Ns, p.tw, tid);
+                else if (R == 5) stockham_pass_bfly<5>(src, dst, ng, Nc, Ns, p.tw, tid);
+                else if (R == 7) stockham_pass_bfly<7>(src, dst, ng, Nc, Ns, p.tw, tid);
+                else
                 for (int e = tid; e < ng * Nc; e += kThreads) {
                     const int f = e / Nc, o = e - f * Nc;
                     const int hi_ = o / NsR, rem = o - hi_ * NsR;

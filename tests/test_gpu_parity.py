@@ -155,6 +155,20 @@ def test_batch_and_ragged(P):
         check_features(outf[i].cpu().numpy(), O.feature_extraction(clips[i], 16000, 800, 400, deltas=False)[0], 400, f"f32 clip {i}")
 
 
+def test_host_pipeline(P):
+    """Pinned-host batch API (chunked copies + kernels on several streams) equals the device-resident path."""
+    import torch
+    from pyaudioanalysis_b200.hostpipe import HostPipeline
+    clips = np.stack([O.synth_clip(200 + i, 16000, 16000) for i in range(7)])
+    host = torch.from_numpy(clips).pin_memory()
+    pipe = HostPipeline(16000, 800, 400, 16000, max_clips=7, device=0, chunk_clips=3, n_streams=2)
+    got = pipe.run(host).clone()
+    ref = P.feature_extraction_batch(torch.from_numpy(clips).cuda(), 16000, 800, 400).cpu()
+    assert torch.equal(got, ref)
+    again = pipe.run(host[:4])
+    assert torch.equal(again, ref[:4])
+
+
 def test_mid_pool_kernel(P):
     import torch
     from pyaudioanalysis_b200.batch import mid_pool_batch
