@@ -134,10 +134,16 @@ struct b200aa_plan {
     std::vector<int> h_blob;
     std::mutex mu;
     std::map<int, std::unique_ptr<Transform>> transforms;   // by transform length
+    // workspace of the host-buffer entry points: grow-only device buffers reused across calls (a cudaMalloc /
+    // cudaFree pair per call costs more than the kernels for a single clip); calls serialise on host_mu
+    std::mutex host_mu;
+    void *ws[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t ws_cap[4] = {0, 0, 0, 0};
     FastTables fast{};                  // extra device tables of the specialised kernel
     ~b200aa_plan()
     {
         if (d_blob) cudaFree(d_blob);
+        for (void *w : ws) if (w) cudaFree(w);
         fast.release();
     }
 };
@@ -684,10 +690,22 @@ extern "C" int b200aa_chromagram(const b200aa_plan *plan, const void *d_sig, int
 // ------------------------------------------------------------------------------------------------
 // host-buffer entry points
 // ------------------------------------------------------------------------------------------------
+// slot i of the plan's workspace, grown to at least n bytes (caller holds host_mu)
 struct DevBuf {
     void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    int alloc(size_t n) { return cudaMalloc(&p, n ? n : 1) == cudaSuccess ? 0 : -1; }
+    int alloc_from(b200aa_plan *pl, int slot, size_t n)
+    {
+        if (pl->ws_cap[slot] < n) {
+            if (pl->ws[slot]) cudaFree(pl->ws[slot]);
+            pl->ws[slot] = nullptr;
+            pl->ws_cap[slot] = 0;
+            const size_t want = n + n / 4 + 4096;
+            if (cudaMalloc(&pl->ws[slot], want) != cudaSuccess) return -1;
+            pl->ws_cap[slot] = want;
+        }
+        p = pl->ws[slot];
+        return 0;
+    }
 };
 
 extern "C" int b200aa_st_features_host(const b200aa_plan *plan, const void *h_sig, int dtype, int64_t n_clips,
@@ -698,8 +716,10 @@ extern "C" int b200aa_st_features_host(const b200aa_plan *plan, const void *h_si
     if (T == 0) return B200AA_ERR_TOO_SHORT;
     const int F = deltas ? 68 : 34;
     const size_t in_b = size_t(n_clips) * n_samples * (dtype == 0 ? 2 : 4), out_b = size_t(n_clips) * F * T * 4;
+    b200aa_plan *pl = const_cast<b200aa_plan *>(plan);
+    std::lock_guard<std::mutex> hold(pl->host_mu);
     DevBuf sig, nm, out;
-    if (sig.alloc(in_b) || nm.alloc(sizeof(b200aa_clip_norm) * n_clips) || out.alloc(out_b))
+    if (sig.alloc_from(pl, 0, in_b) || nm.alloc_from(pl, 1, sizeof(b200aa_clip_norm) * n_clips) || out.alloc_from(pl, 2, out_b))
         return cuda_fail(cudaGetLastError(), "cudaMalloc");
     cudaStream_t st = nullptr;
     CK(cudaMemcpyAsync(sig.p, h_sig, in_b, cudaMemcpyHostToDevice, st));
@@ -719,8 +739,11 @@ extern "C" int b200aa_spectrogram_host(const b200aa_plan *plan, const void *h_si
     const int64_t R = b200aa_spectrogram_rows(n_samples, plan->window, plan->step);
     if (R <= 0) return B200AA_ERR_TOO_SHORT;
     const size_t in_b = size_t(n_samples) * (dtype == 0 ? 2 : 4), out_b = size_t(R) * plan->K * 4;
+    b200aa_plan *pl = const_cast<b200aa_plan *>(plan);
+    std::lock_guard<std::mutex> hold(pl->host_mu);
     DevBuf sig, nm, out;
-    if (sig.alloc(in_b) || nm.alloc(sizeof(b200aa_clip_norm)) || out.alloc(out_b)) return cuda_fail(cudaGetLastError(), "cudaMalloc");
+    if (sig.alloc_from(pl, 0, in_b) || nm.alloc_from(pl, 1, sizeof(b200aa_clip_norm)) || out.alloc_from(pl, 2, out_b))
+        return cuda_fail(cudaGetLastError(), "cudaMalloc");
     cudaStream_t st = nullptr;
     CK(cudaMemcpyAsync(sig.p, h_sig, in_b, cudaMemcpyHostToDevice, st));
     int rc = b200aa_clip_stats(sig.p, dtype, 1, n_samples, n_samples, nullptr, (b200aa_clip_norm *)nm.p, st);
@@ -738,8 +761,11 @@ extern "C" int b200aa_chromagram_host(const b200aa_plan *plan, const void *h_sig
     const int64_t R = b200aa_chromagram_rows(n_samples, plan->window, plan->step);
     if (R <= 0 || n_samples - plan->step - plan->window < 0) return B200AA_ERR_TOO_SHORT;
     const size_t in_b = size_t(n_samples) * (dtype == 0 ? 2 : 4), out_b = size_t(R) * 12 * 4;
+    b200aa_plan *pl = const_cast<b200aa_plan *>(plan);
+    std::lock_guard<std::mutex> hold(pl->host_mu);
     DevBuf sig, nm, out;
-    if (sig.alloc(in_b) || nm.alloc(sizeof(b200aa_clip_norm)) || out.alloc(out_b)) return cuda_fail(cudaGetLastError(), "cudaMalloc");
+    if (sig.alloc_from(pl, 0, in_b) || nm.alloc_from(pl, 1, sizeof(b200aa_clip_norm)) || out.alloc_from(pl, 2, out_b))
+        return cuda_fail(cudaGetLastError(), "cudaMalloc");
     cudaStream_t st = nullptr;
     CK(cudaMemcpyAsync(sig.p, h_sig, in_b, cudaMemcpyHostToDevice, st));
     int rc = b200aa_clip_stats(sig.p, dtype, 1, n_samples, n_samples, nullptr, (b200aa_clip_norm *)nm.p, st);
@@ -759,8 +785,11 @@ extern "C" int b200aa_mid_features_host(const b200aa_plan *plan, const void *h_s
     if (T == 0) return B200AA_ERR_TOO_SHORT;
     const int64_t M = b200aa_mid_windows(T, step_ratio);
     const size_t in_b = size_t(n_samples) * (dtype == 0 ? 2 : 4), st_b = size_t(68) * T * 4, mid_b = size_t(136) * M * 4;
+    b200aa_plan *pl = const_cast<b200aa_plan *>(plan);
+    std::lock_guard<std::mutex> hold(pl->host_mu);
     DevBuf sig, nm, stb, mid;
-    if (sig.alloc(in_b) || nm.alloc(sizeof(b200aa_clip_norm)) || stb.alloc(st_b) || mid.alloc(mid_b))
+    if (sig.alloc_from(pl, 0, in_b) || nm.alloc_from(pl, 1, sizeof(b200aa_clip_norm)) || stb.alloc_from(pl, 2, st_b) ||
+        mid.alloc_from(pl, 3, mid_b))
         return cuda_fail(cudaGetLastError(), "cudaMalloc");
     cudaStream_t st = nullptr;
     CK(cudaMemcpyAsync(sig.p, h_sig, in_b, cudaMemcpyHostToDevice, st));
