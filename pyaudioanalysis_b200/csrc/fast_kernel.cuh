@@ -219,6 +219,203 @@ __device__ __forceinline__ void spectral_features_k(const float *X, const float 
     __syncwarp();
 }
 
+// ----------------------------------------------------------------------------------------------
+// Half-warp variant of the dense pass: 16 lanes per frame (a warp handles two frames), every lane holds
+// C2 = odd(ceil(K/32)) float2 pairs of consecutive bins, per-bin arithmetic on the FP32x2 pipe.  The
+// fixed per-frame overhead (reductions, scalar math, stores) is paid once per two frames.
+// ----------------------------------------------------------------------------------------------
+template <int K>
+struct HalfShape {
+    static constexpr int C2 = ((K + 31) / 32) | 1;      // float2 per lane (odd => conflict-free 8-byte loads)
+    static constexpr int CB = 2 * C2;                   // bins per lane
+    static constexpr int Lb = K / 10;
+    static_assert(16 * CB == DenseShape<K>::Kp, "same padded row length as the warp-per-frame layout");
+    static_assert(CB < Lb && (Lb % 2) == 0, "one (even) entropy block boundary per lane at most");
+};
+template <int K>
+__device__ __forceinline__ DenseLane dense_lane_init_h(int l)        // l = lane within the half-warp, 0..15
+{
+    constexpr int CB = HalfShape<K>::CB, Lb = HalfShape<K>::Lb;
+    DenseLane d;
+    const int k0 = l * CB;
+    const int bnd = ((k0 + CB - 1) / Lb) * Lb;
+    d.split = bnd > k0 ? (bnd - k0) / 2 : 0;            // in float2 pairs
+    d.ps = 32; d.pe = 0;
+    const int j = l;
+    for (int q = 0; q < 16; ++q) {
+        const int b0 = q * CB, bb = ((b0 + CB - 1) / Lb) * Lb, sp = bb > b0 ? bb - b0 : 0;
+        if (sp > 0 && b0 >= j * Lb && b0 + sp <= (j + 1) * Lb) { d.ps = min(d.ps, 2 * q); d.pe = max(d.pe, 2 * q + 1); }
+        if (b0 + sp >= j * Lb && b0 + CB <= (j + 1) * Lb) { d.ps = min(d.ps, 2 * q + 1); d.pe = max(d.pe, 2 * q + 2); }
+    }
+    if (l >= 10) { d.ps = 0; d.pe = 0; }
+    return d;
+}
+__device__ __forceinline__ float half_sum(float v)      // sum over the 16 lanes of a half-warp (both halves at once)
+{
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int K>
+__device__ __forceinline__ float row_sum_h(const float *X, int l)
+{
+    constexpr int C2 = HalfShape<K>::C2;
+    const float2 *X2 = reinterpret_cast<const float2 *>(X) + l * C2;
+    float sx = 0.f;
+#pragma unroll
+    for (int j = 0; j < C2; ++j) { const float2 v = X2[j]; sx += v.x + v.y; }
+    return half_sum(sx);
+}
+
+template <int K>
+__device__ __forceinline__ void spectral_features_h(const float *X, const float *Xp, float sxp, const float *chroma_raw,
+                                                    const int *dlp, float *parts, float *fv, int l, bool active, float *xsave)
+{
+    constexpr int C2 = HalfShape<K>::C2, CB = HalfShape<K>::CB;
+    const int k0 = l * CB;
+    const int4 dlv = *reinterpret_cast<const int4 *>(dlp);        // {split (pairs), ps, pe, -}
+    const float2 *X2 = reinterpret_cast<const float2 *>(X) + l * C2;
+    const float2 *Xp2 = reinterpret_cast<const float2 *>(Xp) + l * C2;
+    float2 x2[C2];
+#pragma unroll
+    for (int j = 0; j < C2; ++j) x2[j] = X2[j];
+    if (xsave) {
+        float2 *S2 = reinterpret_cast<float2 *>(xsave) + l * C2;
+#pragma unroll
+        for (int j = 0; j < C2; ++j) S2[j] = x2[j];
+    }
+    // ---- sums (same per-lane order as row_sum_h)
+    float sx = 0.f, s1 = 0.f, sb = 0.f;
+    float2 plo2 = make_float2(0.f, 0.f), phi2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < C2; ++j) {
+        const float t = x2[j].x + x2[j].y;
+        sx += t;
+        s1 = fmaf(float(2 * j + 1), t, s1);          // (2j+1) a + (2j+2) b = (2j+1)(a+b) + b
+        sb += x2[j].y;
+        const float2 sq = __fmul2_rn(x2[j], x2[j]);
+        if (j < dlv.x) plo2 = f2add(plo2, sq); else phi2 = f2add(phi2, sq);
+    }
+    const float plo = plo2.x + plo2.y, phi = phi2.x + phi2.y, part = plo + phi;
+    float sk = fmaf(float(k0), sx, s1 + sb);         // sum (k0 + i + 1) x_i
+    parts[2 * l] = plo;
+    parts[2 * l + 1] = phi;
+    {   // two sums in 4 exchanges: lanes 0-7 of the half end up with sum(sx), lanes 8-15 with sum(sk)
+        const bool up = l & 8;
+        float keep = up ? sk : sx;
+        const float give = up ? sx : sk;
+        keep += __shfl_xor_sync(0xffffffffu, give, 8);
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+        sx = __shfl_sync(0xffffffffu, keep, 0, 16);
+        sk = __shfl_sync(0xffffffffu, keep, 8, 16);
+    }
+    float incl = part;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const float n = __shfl_up_sync(0xffffffffu, incl, o, 16);
+        if (l >= o) incl += n;
+    }
+    const float sxx = __shfl_sync(0xffffffffu, incl, 15, 16);
+    constexpr float invK = 1.f / float(K);
+    const float cen = sx > 0.f ? fdiv(sk, sx) * invK : 0.f;
+    // ---- spread, flux, rolloff count
+    const float nx = fdiv(1.f, sx + float(K) * B200AA_EPS);
+    const float np_ = fdiv(1.f, sxp + float(K) * B200AA_EPS);
+    const float thr = 0.90f * sxx - B200AA_EPS;
+    float2 d2 = make_float2(float(k0 + 1) * invK - cen, float(k0 + 2) * invK - cen);
+    const float2 dstep = make_float2(2.f * invK, 2.f * invK);
+    const float2 nx2 = make_float2(nx, nx), mnp2 = make_float2(-np_, -np_);
+    float2 sp2 = make_float2(0.f, 0.f), fl2 = make_float2(0.f, 0.f);
+    float run = incl - part, below = 0.f;
+#pragma unroll
+    for (int j = 0; j < C2; ++j) {
+        sp2 = __ffma2_rn(__fmul2_rn(d2, d2), x2[j], sp2);
+        d2 = f2add(d2, dstep);
+        const float2 df = __ffma2_rn(x2[j], nx2, __fmul2_rn(Xp2[j], mnp2));
+        fl2 = __ffma2_rn(df, df, fl2);
+        // padding bins never count: at the last real bin the running sum equals sxx > thr (or everything is 0)
+        run = fmaf(x2[j].x, x2[j].x, run);
+        below += run > thr ? 0.f : 1.f;
+        run = fmaf(x2[j].y, x2[j].y, run);
+        below += run > thr ? 0.f : 1.f;
+    }
+    const float sp = sp2.x + sp2.y, fl = fl2.x + fl2.y;
+    // ---- spectral entropy: lanes 0..9 of the half add up the parts of their block
+    __syncwarp();
+    float e = 0.f;
+    constexpr int MAXP = 2 * (HalfShape<K>::Lb / CB + 2);
+#pragma unroll
+    for (int q = 0; q < MAXP; ++q) e += (dlv.y + q < dlv.z) ? parts[dlv.y + q] : 0.f;
+    float ent = 0.f;
+    if (l < 10) {
+        const float sj = fdiv(e, sxx + B200AA_EPS);
+        ent = -sj * flog2(sj + B200AA_EPS);
+    }
+    const float ch = l < 12 ? fdiv(chroma_raw[l], sxx == 0.f ? B200AA_EPS : sxx) : 0.f;
+    // four sums in 4 exchanges: lanes 0-3 spread, 4-7 flux, 8-11 rolloff count, 12-15 entropy
+    float q4;
+    {
+        const bool up8 = l & 8, up4 = l & 4;
+        float k0_ = up8 ? below : sp, k1_ = up8 ? ent : fl;
+        const float g0_ = up8 ? sp : below, g1_ = up8 ? fl : ent;
+        k0_ += __shfl_xor_sync(0xffffffffu, g0_, 8);
+        k1_ += __shfl_xor_sync(0xffffffffu, g1_, 8);
+        float kk = up4 ? k1_ : k0_;
+        const float gg = up4 ? k0_ : k1_;
+        kk += __shfl_xor_sync(0xffffffffu, gg, 4);
+        kk += __shfl_xor_sync(0xffffffffu, kk, 2);
+        kk += __shfl_xor_sync(0xffffffffu, kk, 1);
+        q4 = kk;
+    }
+    const float mean = half_sum(ch) * (1.f / 12.f);
+    const float dv = l < 12 ? ch - mean : 0.f;
+    const float var = half_sum(dv * dv) * (1.f / 12.f);
+    if (active) {
+        if (l < 12) fv[21 + l] = ch;
+        if (l == 0) {
+            fv[3] = cen;
+            fv[4] = sx > 0.f ? fsqrt_pos(fdiv(q4, sx)) : 0.f;
+            fv[33] = fsqrt_pos(var);
+            fv[34] = sx;
+        }
+        if (l == 4) fv[6] = q4;
+        if (l == 8) fv[7] = q4 >= float(K) ? 0.f : q4 * invK;
+        if (l == 12) fv[5] = q4;
+    }
+    __syncwarp();
+}
+
+// time-domain rows of two frames per warp (half-warp each; lanes 0..9 of a half own the ten entropy blocks)
+template <int N>
+__device__ __forceinline__ void time_features_runs_h(const float *runE, const int *runF, float *fv, int l, bool active)
+{
+    constexpr int RPB = N / 80;
+    float e = 0.f;
+    int f = 0;
+    if (l < 10) {
+#pragma unroll
+        for (int i = 0; i < RPB; ++i) {
+            e += runE[l * RPB + i];
+            const int w = runF[l * RPB + i];
+            f += (w & 0xff) + (w >> 8);
+        }
+    }
+    const float tot = half_sum(e);
+    int ft = f;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) ft += __shfl_xor_sync(0xffffffffu, ft, o);
+    ft -= runF[0] >> 8;
+    const float sj = fdiv(e, tot + B200AA_EPS);
+    float H = l < 10 ? -sj * flog2(sj + B200AA_EPS) : 0.f;
+    H = half_sum(H);
+    if (active && l == 0) {
+        fv[0] = float(ft) * 0.5f / float(N - 1);
+        fv[1] = tot / float(N);
+        fv[2] = H;
+    }
+}
+
 // ---- flat phase 1 (all 256 threads, 8 frames): threads 0..159 = (frame, mel filter pair) -> log10 mel
 // energies; threads 160..255 = (frame, pitch class) -> raw chroma tap sums.  Filters are paired
 // long-with-short on the host so every thread sees about the same number of taps.
@@ -537,8 +734,8 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
     for (int i = tid; i < Nc / 2 + 1; i += NT) s_twp[i] = g_twp[i];
     __syncthreads();
     const SmallTables tb = bind_tables(blob_s, p.bl);
-    if (tid < 32) {
-        const DenseLane d0_ = dense_lane_init<K>(tid);
+    if (tid < (RUNS ? 16 : 32)) {       // RUNS kernels use the half-warp dense pass
+        const DenseLane d0_ = RUNS ? dense_lane_init_h<K>(tid) : dense_lane_init<K>(tid);
         sm.dlane[tid * 4 + 0] = d0_.split; sm.dlane[tid * 4 + 1] = d0_.ps; sm.dlane[tid * 4 + 2] = d0_.pe;
     }
     for (int i = tid; i < 2 * Kp; i += NT) Xprev[i] = 0.f;
@@ -733,6 +930,30 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
             flat_mel_chroma<G>(Xrows, Kp, ng, tb, blob_s + p.bl.mel_pairs, mscr, chr, tid);
             __syncthreads();
             flat_dct<G>(mscr, ng, tb, fvrows, fbase, tid);
+            if (RUNS) {
+                // warps 0..G/2-1: spectral rows of frames (2w, 2w+1); warps G/2..G-1: time-domain rows of the same pairs
+                const int half = lane >> 4, l16 = lane & 15;
+                const int wv = warp < G / 2 ? warp : warp - G / 2;
+                const int fq = 2 * wv + half;
+                const bool act = fq < ng;
+                const int f = act ? fq : 0;                         // inactive halves shadow frame 0 (no stores)
+                const fidx_t fr = g0 + f;
+                int rr = fbase + 1 + f;
+                if (rr > G) rr -= G + 1;
+                float *fv = fvrows + rr * kFvStride;
+                if (warp >= G / 2) {
+                    time_features_runs_h<N>(runE + (f * step) / 8, runF + (f * step) / 8, fv, l16, act);
+                } else {
+                    const float *X = Xrows + size_t(f) * Kp;
+                    const bool has_prev = (fr > 0) && !(f == 0 && g0 == t0 - halo);
+                    const float *Xp = has_prev ? (f > 0 ? Xrows + size_t(f - 1) * Kp : Xprev + xsel * Kp) : X;
+                    // the neighbour's row sum is produced concurrently by another half-warp: recompute it in the same order
+                    const float rs = row_sum_h<K>(Xp, l16);
+                    const float sxp = (has_prev && f == 0) ? fvrows[fbase * kFvStride + 34] : rs;
+                    spectral_features_h<K>(X, Xp, sxp, chr + f * 12, sm.dlane + l16 * 4, parts + (warp * 2 + half) * 32, fv, l16, act,
+                                           (act && f == ng - 1) ? Xprev + (xsel ^ 1) * Kp : nullptr);
+                }
+            } else
             for (int f = warp; f < ng; f += G) {
                 const fidx_t fr = g0 + f;
                 const float *X = Xrows + size_t(f) * Kp;
