@@ -56,37 +56,6 @@ __device__ __forceinline__ float fsqrt_pos(float x) { return x * rsqrtf(fmaxf(x,
 __device__ __forceinline__ float flog2(float x) { return __log2f(x); }
 #endif
 
-// two sums with 5 exchanges + 2 broadcasts (instead of 10 exchanges)
-__device__ __forceinline__ void warp_sum2(float &a, float &b, int lane)
-{
-    const bool up = lane & 16;
-    float keep = up ? b : a;
-    const float give = up ? a : b;
-    keep += __shfl_xor_sync(0xffffffffu, give, 16);
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
-    a = __shfl_sync(0xffffffffu, keep, 0);
-    b = __shfl_sync(0xffffffffu, keep, 16);
-}
-// four sums with 5 exchanges; the totals end up in lanes 0 (a), 8 (b), 16 (c), 24 (d) -- and in every
-// lane of the same 8-lane group
-__device__ __forceinline__ float warp_sum4_grouped(float a, float b, float c, float d, int lane)
-{
-    const bool up16 = lane & 16, up8 = lane & 8;
-    // first exchange: lower half keeps (a, b), upper half keeps (c, d)
-    float k0 = up16 ? c : a, k1 = up16 ? d : b;
-    const float g0 = up16 ? a : c, g1 = up16 ? b : d;
-    k0 += __shfl_xor_sync(0xffffffffu, g0, 16);
-    k1 += __shfl_xor_sync(0xffffffffu, g1, 16);
-    // second exchange: within each half, lower quarter keeps k0, upper quarter keeps k1
-    float k = up8 ? k1 : k0;
-    const float g = up8 ? k0 : k1;
-    k += __shfl_xor_sync(0xffffffffu, g, 8);
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) k += __shfl_xor_sync(0xffffffffu, k, o);
-    return k;
-}
-
 template <int K>
 struct DenseShape {
     static constexpr int C = ((K + 31) / 32) | 1;   // bins per lane (odd => conflict-free chunk loads)
@@ -94,131 +63,11 @@ struct DenseShape {
     static constexpr int Lb = K / 10;               // spectral-entropy block length (:94)
 };
 
-// plain sum of a |X| row in exactly the order spectral_features_k uses (lane chunks, then butterfly),
-// so a frame's flux is bit-identical no matter where the frame sits inside a CTA step
-template <int K>
-__device__ __forceinline__ float row_sum_k(const float *X, int lane)
-{
-    constexpr int C = DenseShape<K>::C;
-    const int k0 = lane * C;
-    float sx = 0.f;
-#pragma unroll
-    for (int i = 0; i < C; ++i) sx += X[k0 + i];
-    return warp_sum(sx);
-}
-
 // per-lane constants of the dense pass (depend on the lane only; computed once per CTA)
 struct DenseLane {
     int split;        // bins [0, split) of the lane's chunk belong to the previous entropy block
     int ps, pe;       // lanes 0..9: range of "parts" (2 per lane, in bin order) that make up block `lane`
 };
-template <int K>
-__device__ __forceinline__ DenseLane dense_lane_init(int lane)
-{
-    constexpr int C = DenseShape<K>::C, Lb = DenseShape<K>::Lb;
-    static_assert(C < Lb, "a lane may straddle at most one entropy block boundary");
-    DenseLane d;
-    const int k0 = lane * C;
-    const int bnd = ((k0 + C - 1) / Lb) * Lb;
-    d.split = bnd > k0 ? bnd - k0 : 0;
-    d.ps = 64; d.pe = 0;
-    const int j = lane;
-    for (int l = 0; l < 32; ++l) {
-        const int b0 = l * C, bb = ((b0 + C - 1) / Lb) * Lb, sp = bb > b0 ? bb - b0 : 0;
-        // part 2l = [b0, b0+sp), part 2l+1 = [b0+sp, b0+C)
-        if (sp > 0 && b0 >= j * Lb && b0 + sp <= (j + 1) * Lb) { d.ps = min(d.ps, 2 * l); d.pe = max(d.pe, 2 * l + 1); }
-        if (b0 + sp >= j * Lb && b0 + C <= (j + 1) * Lb) { d.ps = min(d.ps, 2 * l + 1); d.pe = max(d.pe, 2 * l + 2); }
-    }
-    if (lane >= 10) { d.ps = 0; d.pe = 0; }
-    return d;
-}
-
-template <int K>
-__device__ __forceinline__ void spectral_features_k(const float *X, const float *Xp, float sxp, const float *chroma_raw,
-                                                    const int *dlp, float *parts, float *fv, int lane, float *xsave)
-{
-    constexpr int C = DenseShape<K>::C;
-    const int k0 = lane * C;
-    const int4 dlv = *reinterpret_cast<const int4 *>(dlp);        // {split, ps, pe, -}
-    DenseLane dl; dl.split = dlv.x; dl.ps = dlv.y; dl.pe = dlv.z;
-    float x[C];
-#pragma unroll
-    for (int i = 0; i < C; ++i) x[i] = X[k0 + i];
-    if (xsave) {                                     // last frame of the step: keep |X| for the next step's flux
-#pragma unroll
-        for (int i = 0; i < C; ++i) xsave[k0 + i] = x[i];
-    }
-    // ---- sums: sum X, sum (k+1) X, sum X^2 split at the entropy-block boundary inside the chunk
-    float sx = 0.f, s1 = 0.f, plo = 0.f, phi = 0.f;
-#pragma unroll
-    for (int i = 0; i < C; ++i) {
-        sx += x[i];
-        s1 = fmaf(float(i + 1), x[i], s1);
-        const float sq = x[i] * x[i];
-        if (i < dl.split) plo += sq; else phi += sq;
-    }
-    float sk = fmaf(float(k0), sx, s1);            // sum (k0 + i + 1) x_i
-    const float part = plo + phi;
-    parts[2 * lane] = plo;
-    parts[2 * lane + 1] = phi;
-    warp_sum2(sx, sk, lane);
-    float incl = part;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const float n = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += n;
-    }
-    const float sxx = __shfl_sync(0xffffffffu, incl, 31);
-    constexpr float invK = 1.f / float(K);
-    const float cen = sx > 0.f ? fdiv(sk, sx) * invK : 0.f;
-    // ---- spread, flux, rolloff count in one register pass
-    const float nx = fdiv(1.f, sx + float(K) * B200AA_EPS);
-    const float np_ = fdiv(1.f, sxp + float(K) * B200AA_EPS);
-    const float thr = 0.90f * sxx - B200AA_EPS;    // cumsum + eps > 0.9 E  <=>  cumsum > 0.9 E - eps
-    const float base = float(k0 + 1) * invK - cen;
-    float sp = 0.f, fl = 0.f, run = incl - part, below = 0.f;
-#pragma unroll
-    for (int i = 0; i < C; ++i) {
-        const float d = fmaf(float(i), invK, base);
-        sp = fmaf(d * d, x[i], sp);
-        const float df = fmaf(x[i], nx, -Xp[k0 + i] * np_);
-        fl = fmaf(df, df, fl);
-        run = fmaf(x[i], x[i], run);
-        // cumulative sums are non-decreasing, so the index of the first bin whose cumsum + eps exceeds the
-        // threshold equals the number of (real) bins that do not exceed it (:134-137); padding bins never count
-        below += (run > thr || k0 + i >= K) ? 0.f : 1.f;
-    }
-    // ---- spectral entropy: lanes 0..9 add up the parts of their block (parts are in bin order)
-    __syncwarp();
-    float e = 0.f;
-    constexpr int MAXP = 2 * (DenseShape<K>::Lb / C + 2);
-#pragma unroll
-    for (int q = 0; q < MAXP; ++q) e += (dl.ps + q < dl.pe) ? parts[dl.ps + q] : 0.f;
-    float ent = 0.f;
-    if (lane < 10) {
-        const float sj = fdiv(e, sxx + B200AA_EPS);
-        ent = -sj * flog2(sj + B200AA_EPS);
-    }
-    // chroma: the 12 raw tap sums of this frame were produced by the flat phase (chroma_raw)
-    const float ch = lane < 12 ? fdiv(chroma_raw[lane], sxx == 0.f ? B200AA_EPS : sxx) : 0.f;
-    // totals: lanes 0-7 spread, 8-15 flux, 16-23 rolloff count, 24-31 entropy
-    const float q4 = warp_sum4_grouped(sp, fl, below, ent, lane);
-    const float mean = warp_sum(ch) * (1.f / 12.f);
-    const float dv = lane < 12 ? ch - mean : 0.f;
-    const float var = warp_sum(dv * dv) * (1.f / 12.f);
-    if (lane < 12) fv[21 + lane] = ch;
-    if (lane == 0) {
-        fv[3] = cen;
-        fv[4] = sx > 0.f ? fsqrt_pos(fdiv(q4, sx)) : 0.f;
-        fv[33] = fsqrt_pos(var);
-        fv[34] = sx;                                 // kept with the row: the next frame's flux needs it
-    }
-    if (lane == 8) fv[6] = q4;
-    if (lane == 16) fv[7] = q4 >= float(K) ? 0.f : q4 * invK;
-    if (lane == 24) fv[5] = q4;
-    __syncwarp();
-}
-
 // ----------------------------------------------------------------------------------------------
 // Half-warp variant of the dense pass: 16 lanes per frame (a warp handles two frames), every lane holds
 // C2 = odd(ceil(K/32)) float2 pairs of consecutive bins, per-bin arithmetic on the FP32x2 pipe.  The
@@ -606,36 +455,6 @@ __device__ __forceinline__ void stage_run_smem(const short *raw8, bool has_pred,
     *runF = int(fl) | (int(linkf) << 8);
 }
 
-// zcr, energy, energy entropy of one frame from its runs (warp; lanes 0..9 own the 10 entropy blocks)
-template <int N>
-__device__ __forceinline__ void time_features_runs(const float *runE, const int *runF, float *fv, int lane)
-{
-    constexpr int RPB = N / 80;            // runs per entropy block (block = N/10 samples = RPB runs)
-    float e = 0.f;
-    int f = 0;
-    if (lane < 10) {
-#pragma unroll
-        for (int i = 0; i < RPB; ++i) {
-            e += runE[lane * RPB + i];
-            const int w = runF[lane * RPB + i];
-            f += (w & 0xff) + (w >> 8);
-        }
-    }
-    const float tot = warp_sum(e);
-    int ft = f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ft += __shfl_xor_sync(0xffffffffu, ft, o);
-    ft -= runF[0] >> 8;                    // the pair (frame start - 1, frame start) is not part of the frame
-    const float sj = fdiv(e, tot + B200AA_EPS);
-    float H = lane < 10 ? -sj * flog2(sj + B200AA_EPS) : 0.f;
-    H = warp_sum(H);
-    if (lane == 0) {
-        fv[0] = float(ft) * 0.5f / float(N - 1);
-        fv[1] = tot / float(N);
-        fv[2] = H;
-    }
-}
-
 // ----------------------------------------------------------------------------------------------
 // kernel
 // ----------------------------------------------------------------------------------------------
@@ -734,8 +553,8 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
     for (int i = tid; i < Nc / 2 + 1; i += NT) s_twp[i] = g_twp[i];
     __syncthreads();
     const SmallTables tb = bind_tables(blob_s, p.bl);
-    if (tid < (RUNS ? 16 : 32)) {       // RUNS kernels use the half-warp dense pass
-        const DenseLane d0_ = RUNS ? dense_lane_init_h<K>(tid) : dense_lane_init<K>(tid);
+    if (tid < 16) {
+        const DenseLane d0_ = dense_lane_init_h<K>(tid);
         sm.dlane[tid * 4 + 0] = d0_.split; sm.dlane[tid * 4 + 1] = d0_.ps; sm.dlane[tid * 4 + 2] = d0_.pe;
     }
     for (int i = tid; i < 2 * Kp; i += NT) Xprev[i] = 0.f;
@@ -930,7 +749,7 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
             flat_mel_chroma<G>(Xrows, Kp, ng, tb, blob_s + p.bl.mel_pairs, mscr, chr, tid);
             __syncthreads();
             flat_dct<G>(mscr, ng, tb, fvrows, fbase, tid);
-            if (RUNS) {
+            {
                 // warps 0..G/2-1: spectral rows of frames (2w, 2w+1); warps G/2..G-1: time-domain rows of the same pairs
                 const int half = lane >> 4, l16 = lane & 15;
                 const int wv = warp < G / 2 ? warp : warp - G / 2;
@@ -942,7 +761,20 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
                 if (rr > G) rr -= G + 1;
                 float *fv = fvrows + rr * kFvStride;
                 if (warp >= G / 2) {
-                    time_features_runs_h<N>(runE + (f * step) / 8, runF + (f * step) / 8, fv, l16, act);
+                    if (RUNS) {
+                        time_features_runs_h<N>(runE + (f * step) / 8, runF + (f * step) / 8, fv, l16, act);
+                    } else {
+                        // hops that are not whole 8-sample runs: whole warp per frame straight from the samples
+                        for (int u = 0; u < 2; ++u) {
+                            const int fu = 2 * wv + u;
+                            if (fu < ng) {
+                                int ru = fbase + 1 + fu;
+                                if (ru > G) ru -= G + 1;
+                                const float *frs = sS + fu * step;
+                                time_features([&](int n) { return frs[n]; }, N, nm, fvrows + ru * kFvStride, lane);
+                            }
+                        }
+                    }
                 } else {
                     const float *X = Xrows + size_t(f) * Kp;
                     const bool has_prev = (fr > 0) && !(f == 0 && g0 == t0 - halo);
@@ -953,31 +785,6 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
                     spectral_features_h<K>(X, Xp, sxp, chr + f * 12, sm.dlane + l16 * 4, parts + (warp * 2 + half) * 32, fv, l16, act,
                                            (act && f == ng - 1) ? Xprev + (xsel ^ 1) * Kp : nullptr);
                 }
-            } else
-            for (int f = warp; f < ng; f += G) {
-                const fidx_t fr = g0 + f;
-                const float *X = Xrows + size_t(f) * Kp;
-                const bool has_prev = (fr > 0) && !(f == 0 && g0 == t0 - halo);
-                float sxp;
-                const float *Xp;
-                int rr = fbase + 1 + f;
-                if (rr > G) rr -= G + 1;
-                float *fv = fvrows + rr * kFvStride;
-                const float *frs = sS + f * step;
-                if (RUNS) time_features_runs<N>(runE + (f * step) / 8, runF + (f * step) / 8, fv, lane);
-                else time_features([&](int n) { return frs[n]; }, N, nm, fv, lane);
-                if (has_prev && f > 0) {
-                    Xp = Xrows + size_t(f - 1) * Kp;
-                    sxp = row_sum_k<K>(Xp, lane);      // the neighbour's warp produces its own copy concurrently
-                } else if (has_prev) {
-                    Xp = Xprev + xsel * Kp;
-                    sxp = fvrows[fbase * kFvStride + 34];
-                } else {
-                    Xp = X;
-                    sxp = row_sum_k<K>(X, lane);
-                }
-                spectral_features_k<K>(X, Xp, sxp, chr + f * 12, sm.dlane + lane * 4, parts + warp * 64, fv, lane,
-                                       f == ng - 1 ? Xprev + (xsel ^ 1) * Kp : nullptr);
             }
             __syncthreads();
             // ---- store the [n_out x 8] tile: 8 consecutive threads -> 8 consecutive frames of one feature row
