@@ -125,6 +125,12 @@ int b200aa_chromagram(const b200aa_plan *plan, const void *d_sig, int dtype, int
 int b200aa_mid_pool(const float *d_st, int64_t n_clips, int n_feats, int64_t n_frames,
                     int64_t t_stride, int ratio, int step_ratio, float *d_mid, void *stream);
 
+/* Long-term average: d_out float32 [n_clips, n_rows], the mean of every row of
+ * d_mid [n_clips, n_rows, n_windows] over the windows.
+ * Replaces: `mid_features.mean(axis=0)` in directory_feature_extraction (MidTermFeatures.py:200-201). */
+int b200aa_long_term_mean(const float *d_mid, int64_t n_clips, int n_rows, int64_t n_windows,
+                          float *d_out, void *stream);
+
 /* ------------------------------------------------------------------ host entry points --
  * Same operations on HOST buffers: pinned or pageable input is copied to the device, the
  * kernels run, the result is copied back and the call returns after the stream drained.

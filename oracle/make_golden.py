@@ -91,6 +91,26 @@ def main():
     edge["chroma_clipped"] = S.chromagram(cc, 16000, 800, 400)[0]
     edge["spec_16300"] = quiet(S.spectrogram, cc, 16000, 800, 400)[0]
     np.savez_compressed(os.path.join(OUT, "edges.npz"), **edge)
+    # ---- directory_feature_extraction (long-term averaged mid-term vectors per file)
+    # 12 files of each class of the reference's own pytests/test_data/3_class (8 kHz, 1 s clips)
+    import glob
+    import shutil
+    import tempfile
+    dirs = {}
+    for cls in ("music", "silence", "speech"):
+        files = sorted(glob.glob(os.path.join(REFERENCE_ROOT, "pytests", "test_data", "3_class", cls, "*.wav")))[:12]
+        tmp = tempfile.mkdtemp()
+        for f in files:
+            shutil.copy(f, tmp)
+        feats, flist, names = quiet(M.directory_feature_extraction, tmp, 1.0, 1.0, 0.05, 0.05, compute_beat=False)
+        xs = np.stack([A.read_audio_file(f)[1] for f in sorted(glob.glob(os.path.join(tmp, "*.wav")))])
+        dirs[cls + "_x"] = xs
+        dirs[cls + "_files"] = np.array([os.path.basename(f) for f in flist])
+        dirs[cls + "_feats"] = feats
+        dirs["names"] = np.array(names)
+        shutil.rmtree(tmp)
+    dirs["fs"] = 8000
+    np.savez_compressed(os.path.join(OUT, "dirs.npz"), **dirs)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

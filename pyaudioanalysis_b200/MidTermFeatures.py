@@ -1,5 +1,10 @@
-"""Drop-in for ``pyAudioAnalysis.MidTermFeatures.mid_feature_extraction`` (MidTermFeatures.py:87-127)."""
+"""Drop-in for ``pyAudioAnalysis.MidTermFeatures.mid_feature_extraction`` (MidTermFeatures.py:87-127) and the
+directory wrappers around it (``directory_feature_extraction`` :140-221, ``multiple_directory_feature_extraction``
+:224-260): file decode stays on the host (scipy.io.wavfile, like audioBasicIO.read_audio_file for .wav), files of
+equal sampling rate and length are batched into single GPU launches."""
 import ctypes
+import glob
+import os
 
 import numpy as np
 
@@ -33,3 +38,95 @@ def mid_feature_extraction(signal, sampling_rate, mid_window, mid_step, short_wi
     st_names = ShortTermFeatures.feature_names(True)
     names = [n + "_mean" for n in st_names] + [n + "_std" for n in st_names]
     return mid.astype(np.float64), st.astype(np.float64), names
+
+
+VERBOSE = True      # the reference prints one "Analyzing file ..." line per file
+
+
+def _read_wav(path):
+    """audioBasicIO.read_audio_file for .wav (:99) + stereo_to_mono (:156-168)."""
+    from scipy.io import wavfile
+    fs, x = wavfile.read(path)
+    if x.ndim == 2:
+        if x.shape[1] == 1:
+            x = x.flatten()
+        elif x.shape[1] == 2:
+            x = (x[:, 1] / 2) + (x[:, 0] / 2)
+    return fs, x
+
+
+def directory_feature_extraction(folder_path, mid_window, mid_step, short_window, short_step, compute_beat=True):
+    """One long-term averaged 136-vector per audio file of a folder (reference MidTermFeatures.py:140-221).
+
+    Window arguments are in seconds.  Returns (features [n_files x 136] -- a 1-D vector for a single file and an
+    empty array for none, exactly like the reference's np.vstack logic --, file list, feature names).  Only .wav
+    files are decoded here (other containers need ffmpeg / pydub on the host and are skipped with a note), and the
+    beat features of ``compute_beat=True`` are outside the GPU path.
+    """
+    import torch
+    from .batch import mid_feature_extraction_batch, long_term_mean_batch
+    if compute_beat:
+        raise NotImplementedError("compute_beat=True (beat_extraction / peakdet) is not part of the GPU path; "
+                                  "call with compute_beat=False as multiple_directory_feature_extraction does")
+    types = ('*.wav', '*.aif', '*.aiff', '*.mp3', '*.au', '*.ogg')
+    files = []
+    for t in types:
+        files.extend(glob.glob(os.path.join(folder_path, t)))
+    files = sorted(files)
+    kept, signals = [], []
+    for i, path in enumerate(files):
+        if VERBOSE:
+            print("Analyzing file {0:d} of {1:d}: {2:s}".format(i + 1, len(files), path))
+        if os.stat(path).st_size == 0:
+            if VERBOSE:
+                print("   (EMPTY FILE -- SKIPPING)")
+            continue
+        if os.path.splitext(path)[1].lower() != ".wav":
+            print("   (only .wav is decoded by pyaudioanalysis_b200 -- SKIPPING)")
+            continue
+        fs, x = _read_wav(path)
+        if fs == 0:
+            continue
+        if x.shape[0] < float(fs) / 5:
+            if VERBOSE:
+                print("  (AUDIO FILE TOO SMALL - SKIPPING)")
+            continue
+        kept.append(path)
+        signals.append((fs, x))
+    names = []
+    if not kept:
+        return np.array([]), [], names
+    st_names = ShortTermFeatures.feature_names(True)
+    names = [n + "_mean" for n in st_names] + [n + "_std" for n in st_names]
+    # batch files that share (sampling rate, length, sample format)
+    vectors = [None] * len(kept)
+    groups = {}
+    for idx, (fs, x) in enumerate(signals):
+        clip, code = _as_clip(x)
+        groups.setdefault((int(fs), clip.shape[0], code), []).append((idx, clip))
+    for (fs, n, code), members in groups.items():
+        host = np.stack([c for _, c in members])
+        dev = torch.from_numpy(host).cuda()
+        mid, _ = mid_feature_extraction_batch(dev, fs, round(mid_window * fs), round(mid_step * fs),
+                                              round(fs * short_window), round(fs * short_step))
+        lt = long_term_mean_batch(mid).cpu().numpy().astype(np.float64)
+        for (idx, _), v in zip(members, lt):
+            vectors[idx] = v
+    out, out_files = np.array([]), []
+    for path, v in zip(kept, vectors):
+        out_files.append(path)
+        if (not np.isnan(v).any()) and (not np.isinf(v).any()):      # reference :203-204
+            out = v if len(out) == 0 else np.vstack((out, v))
+    return out, out_files, names
+
+
+def multiple_directory_feature_extraction(path_list, mid_window, mid_step, short_window, short_step, compute_beat=False):
+    """Reference MidTermFeatures.py:224-260: one feature matrix per class folder."""
+    features, class_names, file_names = [], [], []
+    for d in path_list:
+        f, fn, _ = directory_feature_extraction(d, mid_window, mid_step, short_window, short_step, compute_beat=compute_beat)
+        if f.shape[0] > 0:
+            features.append(f)
+            file_names.append(fn)
+            class_names.append(d.split(os.sep)[-2] if d[-1] == os.sep else d.split(os.sep)[-1])
+    return features, class_names, file_names

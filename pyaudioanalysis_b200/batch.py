@@ -106,6 +106,18 @@ def mid_pool_batch(st, ratio, step_ratio, n_frames=None):
     return mid
 
 
+def long_term_mean_batch(mid):
+    """Mean over the mid-term windows: CUDA float32 [B, rows, M] -> [B, rows] (MidTermFeatures.py:200-201)."""
+    _require_cuda(mid, "mid")
+    if mid.dim() != 3 or mid.dtype != torch.float32 or not mid.is_contiguous():
+        raise ValueError("mid must be contiguous float32 [B, rows, M]")
+    B, rows, M = mid.shape
+    with torch.cuda.device(mid.device):
+        out = torch.empty((B, rows), dtype=torch.float32, device=mid.device)
+        check(lib().b200aa_long_term_mean(ctypes.c_void_p(mid.data_ptr()), B, rows, M, ctypes.c_void_p(out.data_ptr()), _stream()))
+    return out
+
+
 def mid_ratios(mid_window, mid_step, short_window, short_step):
     """MidTermFeatures.py:100-102 (Python round(): half to even).  window/step truncation happens
     inside feature_extraction only (ShortTermFeatures.py:563-564); the ratios use the raw arguments."""

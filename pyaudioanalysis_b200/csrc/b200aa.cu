@@ -525,6 +525,31 @@ extern "C" int b200aa_mid_pool(const float *d_st, int64_t n_clips, int n_feats, 
     return B200AA_OK;
 }
 
+// long-term average of the mid-term matrix: one warp per (clip, row), fp64 accumulation
+__global__ void __launch_bounds__(256) long_term_mean_kernel(const float *mid, int64_t rows_total, int64_t M, float *out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+    if (wid >= rows_total) return;
+    const float *row = mid + size_t(wid) * M;
+    double s = 0.0;
+    for (int64_t c = lane; c < M; c += 32) s += double(row[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[wid] = float(s / double(M));
+}
+
+extern "C" int b200aa_long_term_mean(const float *d_mid, int64_t n_clips, int n_rows, int64_t n_windows, float *d_out, void *stream)
+{
+    if (!d_mid || !d_out || n_clips < 0 || n_rows < 1 || n_windows < 1) return B200AA_ERR_INVALID;
+    const int64_t rows = n_clips * n_rows;
+    if (rows == 0) return B200AA_OK;
+    const int64_t blocks = (rows * 32 + 255) / 256;
+    long_term_mean_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_mid, rows, n_windows, d_out);
+    CK_LAUNCH("long_term_mean_kernel");
+    return B200AA_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernel 1 launchers
 // ------------------------------------------------------------------------------------------------

@@ -18,7 +18,8 @@ def install(pyaudioanalysis_pkg=None):
         ref_st, ref_mt = pyaudioanalysis_pkg.ShortTermFeatures, pyaudioanalysis_pkg.MidTermFeatures
     done = []
     for mod, ours, names in ((ref_st, ours_st, ("feature_extraction", "spectrogram", "chromagram")),
-                             (ref_mt, ours_mt, ("mid_feature_extraction",))):
+                             (ref_mt, ours_mt, ("mid_feature_extraction", "directory_feature_extraction",
+                                                "multiple_directory_feature_extraction"))):
         for n in names:
             _saved.setdefault((mod, n), getattr(mod, n))
             setattr(mod, n, getattr(ours, n))

@@ -155,6 +155,39 @@ def test_batch_and_ragged(P):
         check_features(outf[i].cpu().numpy(), O.feature_extraction(clips[i], 16000, 800, 400, deltas=False)[0], 400, f"f32 clip {i}")
 
 
+def test_directory_feature_extraction(P, tmp_path):
+    """long-term averaged mid-term vectors per file of a folder, against the reference's own output
+    on its 3_class test clips (8 kHz, 1 s, 12 per class; the silence class exercises near-digital-silence audio)."""
+    from scipy.io import wavfile
+    from tests.conftest import load_golden
+    g = load_golden("dirs.npz")
+    P.MidTermFeatures.VERBOSE = False
+    dirs = []
+    for cls in ("music", "silence", "speech"):
+        d = tmp_path / cls
+        d.mkdir()
+        for name, x in zip(g[cls + "_files"], g[cls + "_x"]):
+            wavfile.write(str(d / str(name)), int(g["fs"]), x)
+        dirs.append(str(d))
+        feats, files, names = P.MidTermFeatures.directory_feature_extraction(str(d), 1.0, 1.0, 0.05, 0.05, compute_beat=False)
+        assert names == list(g["names"]) and [f.split("/")[-1] for f in files] == list(g[cls + "_files"])
+        assert feats.shape == (12, 136)
+        check_close(feats, g[cls + "_feats"], f"directory_feature_extraction {cls}", rtol=2e-4, atol=2e-5)
+    f3, classes, fn3 = P.MidTermFeatures.multiple_directory_feature_extraction(dirs, 1.0, 1.0, 0.05, 0.05)
+    assert classes == ["music", "silence", "speech"] and len(f3) == 3 and f3[0].shape == (12, 136)
+    with pytest.raises(NotImplementedError):
+        P.MidTermFeatures.directory_feature_extraction(dirs[0], 1.0, 1.0, 0.05, 0.05)      # compute_beat defaults to True
+    one = tmp_path / "one"
+    one.mkdir()
+    wavfile.write(str(one / "a.wav"), int(g["fs"]), g["music_x"][0])
+    f1, _, _ = P.MidTermFeatures.directory_feature_extraction(str(one), 1.0, 1.0, 0.05, 0.05, compute_beat=False)
+    assert f1.shape == (136,)                       # the reference returns a 1-D vector for a single file
+    empty = tmp_path / "none"
+    empty.mkdir()
+    f0, l0, _ = P.MidTermFeatures.directory_feature_extraction(str(empty), 1.0, 1.0, 0.05, 0.05, compute_beat=False)
+    assert f0.shape == (0,) and l0 == []
+
+
 def test_host_pipeline(P):
     """Pinned-host batch API (chunked copies + kernels on several streams) equals the device-resident path."""
     import torch
