@@ -130,3 +130,85 @@ def multiple_directory_feature_extraction(path_list, mid_window, mid_step, short
             file_names.append(fn)
             class_names.append(d.split(os.sep)[-2] if d[-1] == os.sep else d.split(os.sep)[-1])
     return features, class_names, file_names
+
+
+def _mid_per_file(signals, mid_window, mid_step, short_window, short_step, want_short=False):
+    """Mid-term (and optionally short-term) matrices of a list of (fs, signal); equal (fs, length, format) files share
+    one launch.  Returns a list of (mid float64 [136 x M], st float64 [68 x T] | None) in input order."""
+    import torch
+    from .batch import mid_feature_extraction_batch
+    results = [None] * len(signals)
+    groups = {}
+    for idx, (fs, x) in enumerate(signals):
+        clip, code = _as_clip(x)
+        groups.setdefault((int(fs), clip.shape[0], code), []).append((idx, clip))
+    for (fs, n, code), members in groups.items():
+        dev = torch.from_numpy(np.stack([c for _, c in members])).cuda()
+        mid, st = mid_feature_extraction_batch(dev, fs, round(mid_window * fs), round(mid_step * fs),
+                                               round(fs * short_window), round(fs * short_step))
+        mid_h = mid.cpu().numpy().astype(np.float64)
+        st_h = st.cpu().numpy().astype(np.float64) if want_short else None
+        for k, (idx, _) in enumerate(members):
+            results[idx] = (mid_h[k], st_h[k] if want_short else None)
+    return results
+
+
+def directory_feature_extraction_no_avg(folder_path, mid_window, mid_step, short_window, short_step):
+    """Reference MidTermFeatures.py:263-309: every mid-term vector of every file, no long-term averaging.
+    Returns (X [sum of windows x 136], file index per row, file list)."""
+    files = []
+    for t in ('*.wav', '*.aif', '*.aiff', '*.ogg'):
+        files.extend(glob.glob(os.path.join(folder_path, t)))
+    files = sorted(files)
+    idxs, signals = [], []
+    for i, path in enumerate(files):
+        if os.path.splitext(path)[1].lower() != ".wav":
+            print("   (only .wav is decoded by pyaudioanalysis_b200 -- SKIPPING " + path + ")")
+            continue
+        fs, x = _read_wav(path)
+        if fs == 0:
+            continue
+        idxs.append(i)
+        signals.append((fs, x))
+    mids = _mid_per_file(signals, mid_window, mid_step, short_window, short_step)
+    mid_features, signal_idx = np.array([]), np.array([])
+    for i, (mid, _) in zip(idxs, mids):
+        rows = np.transpose(mid)
+        if len(mid_features) == 0:
+            mid_features = rows
+            signal_idx = np.zeros((rows.shape[0],))          # the reference labels the first block 0 (:301)
+        else:
+            mid_features = np.vstack((mid_features, rows))
+            signal_idx = np.append(signal_idx, i * np.ones((rows.shape[0],)))
+    return mid_features, signal_idx, files
+
+
+def mid_feature_extraction_to_file(file_path, mid_window, mid_step, short_window, short_step, output_file,
+                                   store_short_features=False, store_csv=False, plot=False):
+    """Reference MidTermFeatures.py:324-362: <output>_mt.npy ([136 x M] float64), optional <output>_st.npy
+    ([68 x T]) and transposed CSV copies -- the on-disk formats the reference's CLI consumers read."""
+    fs, x = _read_wav(file_path)
+    (mid, st), = _mid_per_file([(fs, x)], mid_window, mid_step, short_window, short_step, want_short=True)
+    if store_short_features:
+        np.save(output_file + "_st", st)
+        if plot:
+            print("Short-term np file: " + output_file + "_st.npy saved")
+        if store_csv:
+            np.savetxt(output_file + "_st.csv", st.T, delimiter=",")
+            if plot:
+                print("Short-term CSV file: " + output_file + "_st.csv saved")
+    np.save(output_file + "_mt", mid)
+    if plot:
+        print("Mid-term np file: " + output_file + "_mt.npy saved")
+    if store_csv:
+        np.savetxt(output_file + "_mt.csv", mid.T, delimiter=",")
+        if plot:
+            print("Mid-term CSV file: " + output_file + "_mt.csv saved")
+
+
+def mid_feature_extraction_file_dir(folder_path, mid_window, mid_step, short_window, short_step,
+                                    store_short_features=False, store_csv=False, plot=False):
+    """Reference MidTermFeatures.py:365-377."""
+    for f in glob.glob(folder_path + os.sep + '*.wav'):
+        mid_feature_extraction_to_file(f, mid_window, mid_step, short_window, short_step, f,
+                                       store_short_features, store_csv, plot)

@@ -19,7 +19,8 @@ def install(pyaudioanalysis_pkg=None):
     done = []
     for mod, ours, names in ((ref_st, ours_st, ("feature_extraction", "spectrogram", "chromagram")),
                              (ref_mt, ours_mt, ("mid_feature_extraction", "directory_feature_extraction",
-                                                "multiple_directory_feature_extraction"))):
+                                                "multiple_directory_feature_extraction", "directory_feature_extraction_no_avg",
+                                                "mid_feature_extraction_to_file", "mid_feature_extraction_file_dir"))):
         for n in names:
             _saved.setdefault((mod, n), getattr(mod, n))
             setattr(mod, n, getattr(ours, n))

@@ -102,6 +102,18 @@ def main():
     emit({"config": "4 parity spot check (30 s)", "mid_max_abs_err": float(np.abs(gm - rm).max()),
           "mid_max_rel_err_over_1e-3": float((np.abs(gm - rm) / np.maximum(np.abs(rm), 1e-3)).max())})
 
+    # ---- generic (any-window) kernel: config-2 shape with the specialised kernel disabled, and a 25/10 ms window
+    from pyaudioanalysis_b200._lib import Plan
+    cg = noise(1000, 160000, 5)
+    pg = Plan(16000, 800, 400)
+    pg.force_generic(True)
+    msg = timed(lambda: pkg.feature_extraction_batch(cg, 16000, 800, 400, plan=pg), reps=5)
+    ms25 = timed(lambda: pkg.feature_extraction_batch(cg, 16000, 400, 160), reps=5)
+    emit({"config": "generic kernel: 1000 x 10 s @16 kHz", "ms_800_400_forced_generic": msg,
+          "frames_per_s_800_400": 399000 / (msg * 1e-3), "ms_400_160": ms25,
+          "frames_per_s_400_160": 1000 * ((160000 - 400) // 160 + 1) / (ms25 * 1e-3)})
+    del cg
+
     # ---- kernel 0 alone on config 2 (HBM-bound)
     c2 = noise(1000, 160000, 2)
     ms0 = timed(lambda: clip_stats(c2), reps=20)

@@ -188,6 +188,36 @@ def test_directory_feature_extraction(P, tmp_path):
     assert f0.shape == (0,) and l0 == []
 
 
+def test_file_wrappers(P, tmp_path):
+    """no-averaging directory wrapper and the .npy / CSV writers (MidTermFeatures.py:263-377)."""
+    from scipy.io import wavfile
+    P.MidTermFeatures.VERBOSE = False
+    clips = [O.synth_clip(300 + i, n, 16000) for i, n in enumerate((40000, 24000, 40000))]
+    stereo = np.stack([clips[1], clips[1][::-1]], axis=1)            # a 2-channel file: (L/2)+(R/2)
+    d = tmp_path / "wavs"
+    d.mkdir()
+    wavfile.write(str(d / "a.wav"), 16000, clips[0])
+    wavfile.write(str(d / "b.wav"), 16000, stereo)
+    wavfile.write(str(d / "c.wav"), 16000, clips[2])
+    X, idx, files = P.MidTermFeatures.directory_feature_extraction_no_avg(str(d), 1.0, 0.5, 0.05, 0.025)
+    mono_b = (stereo[:, 1] / 2) + (stereo[:, 0] / 2)
+    refs = [O.mid_feature_extraction(c, 16000, 16000, 8000, 800, 400)[0] for c in (clips[0], mono_b, clips[2])]
+    assert X.shape == (sum(r.shape[1] for r in refs), 136) and len(files) == 3
+    check_close(X, np.vstack([r.T for r in refs]), "directory_feature_extraction_no_avg", rtol=2e-4, atol=2e-5)
+    assert list(idx[:refs[0].shape[1]]) == [0.0] * refs[0].shape[1] and idx[-1] == 2.0
+    out = str(tmp_path / "feat")
+    P.MidTermFeatures.mid_feature_extraction_to_file(str(d / "a.wav"), 1.0, 1.0, 0.05, 0.05, out, store_short_features=True, store_csv=True)
+    mt, st = np.load(out + "_mt.npy"), np.load(out + "_st.npy")
+    rm, rs, _ = O.mid_feature_extraction(clips[0], 16000, 16000, 16000, 800, 800)
+    assert mt.dtype == np.float64 and mt.shape == rm.shape and st.shape == rs.shape
+    check_close(mt, rm, "_mt.npy", rtol=2e-4, atol=2e-5)
+    csv = np.loadtxt(out + "_mt.csv", delimiter=",")
+    assert csv.shape == mt.T.shape
+    np.testing.assert_allclose(csv, mt.T, rtol=1e-12)
+    P.MidTermFeatures.mid_feature_extraction_file_dir(str(d), 1.0, 1.0, 0.05, 0.05)
+    assert (d / "c.wav_mt.npy").exists()
+
+
 def test_host_pipeline(P):
     """Pinned-host batch API (chunked copies + kernels on several streams) equals the device-resident path."""
     import torch
