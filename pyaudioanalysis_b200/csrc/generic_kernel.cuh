@@ -47,7 +47,7 @@ __device__ __forceinline__ void stockham_pass_bfly(const float2 *src, float2 *ds
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads) st_generic_kernel(const StParams p)
+__global__ void __launch_bounds__(kThreads, 2) st_generic_kernel(const StParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int G = p.G, Nc = p.Nc, K = p.K, Kp = p.Kp, w = p.window, fn = p.fft_n;
@@ -103,6 +103,20 @@ __global__ void __launch_bounds__(kThreads) st_generic_kernel(const StParams p)
                 bufA[e] = z;
             }
             __syncthreads();
+            if (MODE == kModeFeatures) {
+                // time-domain rows from the staged samples (bufA holds x - x[frame start]; one warp per frame).
+                // fvrows rows of this step are free: the previous step's store loop finished before its last barrier.
+                for (int f = warp; f < ng; f += kWarps) {
+                    const float2 *zf = bufA + size_t(f) * Nc;
+                    const float d0 = rd(origin + (g0 + f) * p.step);
+                    float *fv = fvrows + size_t(f + 1) * kFvStride;
+                    if (p.packed)
+                        time_features([&](int n) { const float2 q = zf[n >> 1]; return ((n & 1) ? q.y : q.x) + d0; }, w, nm, fv, lane);
+                    else
+                        time_features([&](int n) { return zf[n].x + d0; }, w, nm, fv, lane);
+                }
+                // no barrier needed before the passes: they only read bufA as well
+            }
             // ---- Stockham passes
             float2 *src = bufA, *dst = bufB;
             int Ns = 1;
@@ -208,8 +222,6 @@ __global__ void __launch_bounds__(kThreads) st_generic_kernel(const StParams p)
                 float sxp;
                 const float *Xp;
                 float *fv = fvrows + size_t(f + 1) * kFvStride;
-                const int64_t s0 = fr * p.step;
-                time_features([&](int n) { return rd(s0 + n); }, w, nm, fv, lane);
                 if (has_prev && f > 0) {
                     // row sum of the neighbour is produced by another warp in this same phase:
                     // recompute it here instead of synchronising
