@@ -509,7 +509,8 @@ inline size_t fast_smem_bytes(int step, int blob_words, bool runs)
     using S = FastShape<R, G>;
     const size_t span_max = size_t(G - 1) * step + S::N;
     const size_t nrun = (span_max / 8 + 4) & ~size_t(3);
-    const bool zs_alias = runs && size_t(G) * step >= 2 * size_t(G) * S::ZS;   // see the kernel
+    // see the kernel: with run staging the carried tail must survive, otherwise the whole span is dead after pass 1
+    const bool zs_alias = runs ? size_t(G) * step >= 2 * size_t(G) * S::ZS : span_max >= 2 * size_t(G) * S::ZS;
     return fast_fixed_bytes<R, G>() + sizeof(int) * ((blob_words + 3) & ~3) + 2 * sizeof(float) * nrun +
            sizeof(float) * (span_max + 8) + (zs_alias ? 0 : sizeof(float2) * G * S::ZS) +
            (runs ? sizeof(short) * (size_t(G) * step + 16) : 0);
@@ -536,9 +537,10 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
     float *const runE = reinterpret_cast<float *>(blob_s + blob_pad);                 // run partials (RUNS only)
     int *const runF = reinterpret_cast<int *>(runE + nrun);
     float *const sS = reinterpret_cast<float *>(runF + nrun);                         // sample span
-    // published second-pass outputs [G][ZS]: with run partials the samples of the G frames are dead once
-    // pass 1 has read them (only the tail that the next step reuses must survive), so Zs lives on top of them
-    const bool zs_alias = RUNS && G * step >= 2 * G * ZS;
+    // published second-pass outputs [G][ZS]: the float samples of the G frames are dead once pass 1 has read them
+    // (with run staging only the tail that the next step reuses must survive; without it the time-domain rows are
+    // produced right after staging), so Zs lives on top of them
+    const bool zs_alias = RUNS ? (G * step >= 2 * G * ZS) : ((G - 1) * step + N >= 2 * G * ZS);
     float2 *const Zs = zs_alias ? reinterpret_cast<float2 *>(sS)
                                 : reinterpret_cast<float2 *>(sS + (((G - 1) * step + N + 8) & ~3));
     // raw int16 landing zone of the TMA prefetch (RUNS only): 8 predecessor samples + G*step new samples
@@ -638,6 +640,16 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
                 for (int i = tid; i < span; i += NT) sS[i] = rd(sbase + i);
             }
             __syncthreads();
+            if (!RUNS && MODE == kModeFeatures) {
+                // hops that are not whole 8-sample runs: time-domain rows straight from the staged samples, one warp
+                // per frame, BEFORE the FFT (pass 2 reuses the sample buffer)
+                for (int f = warp; f < ng; f += G) {
+                    int ru = fbase + 1 + f;
+                    if (ru > G) ru -= G + 1;
+                    const float *frs = sS + f * step;
+                    time_features([&](int n) { return frs[n]; }, N, nm, fvrows + ru * kFvStride, lane);
+                }
+            }
             // ---- TMA: fetch the next step's new samples (same work item) while this step computes
             prefetched = false;
             if (RUNS && MODE == kModeFeatures && p.dtype == B200AA_DTYPE_I16 && vec_ok && step < N && g0 + G < t1) {
@@ -763,17 +775,6 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
                 if (warp >= G / 2) {
                     if (RUNS) {
                         time_features_runs_h<N>(runE + (f * step) / 8, runF + (f * step) / 8, fv, l16, act);
-                    } else {
-                        // hops that are not whole 8-sample runs: whole warp per frame straight from the samples
-                        for (int u = 0; u < 2; ++u) {
-                            const int fu = 2 * wv + u;
-                            if (fu < ng) {
-                                int ru = fbase + 1 + fu;
-                                if (ru > G) ru -= G + 1;
-                                const float *frs = sS + fu * step;
-                                time_features([&](int n) { return frs[n]; }, N, nm, fvrows + ru * kFvStride, lane);
-                            }
-                        }
                     }
                 } else {
                     const float *X = Xrows + size_t(f) * Kp;
