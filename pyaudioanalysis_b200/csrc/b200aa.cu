@@ -576,7 +576,7 @@ static int launch_generic(const b200aa_plan *pl, StParams &p, int64_t rows_max, 
     size_t smem = 0;
     for (; G >= 1; G >>= 1) {
         smem = generic_smem_bytes(G, p.Nc, p.Kp, p.bl.words);
-        if (smem <= (G == 8 ? 100u * 1024u : 220u * 1024u)) break;
+        if (smem <= (G == 8 ? 100u * 1024u : 226u * 1024u)) break;   // 227 KB is the per-CTA opt-in maximum
     }
     if (G < 1) return B200AA_ERR_UNSUPPORTED;
     p.G = G;

@@ -294,4 +294,75 @@ __device__ __forceinline__ void time_features(Acc D, int w, const b200aa_clip_no
     }
 }
 
+
+// sign(x - mean) in {-1, 0, +1} as a float, from the exact thresholds of b200aa_clip_norm
+__device__ __forceinline__ float sign_class(float d, float lo, float hi) { return (d > lo ? 1.f : 0.f) - (d < hi ? 1.f : 0.f); }
+
+// ---- chunked form of the same three rows: every lane owns c = ceil(w/32) CONSECUTIVE samples (one load per
+// sample, sequential sign flips, energy split at the single entropy-block boundary a chunk can contain); the block
+// energies are then sums of lane parts.  About half the instructions of time_features() above.
+// Per-lane constants (depend on w and the lane only; computed once per CTA into shared memory as int4):
+//   x = c, y = samples of the chunk that belong to the earlier block, [z, w) = parts that make up block `lane` (< 10)
+__device__ inline int4 time_lane_init(int w, int lane)
+{
+    const int c = (w + 31) / 32, L = w / 10;
+    const int k0 = lane * c, end = min(w, k0 + c);
+    int split = 0;
+    if (L > 0 && end > k0) {
+        const int bnd = ((end - 1) / L) * L;
+        split = bnd > k0 ? bnd - k0 : 0;
+    }
+    int ps = 64, pe = 0;
+    if (lane < 10 && L > 0) {
+        const int j = lane;
+        for (int q = 0; q < 32; ++q) {
+            const int b0 = q * c, e0 = min(w, b0 + c);
+            if (e0 <= b0) break;
+            const int bb = ((e0 - 1) / L) * L, sp = bb > b0 ? bb - b0 : 0;
+            if (sp > 0 && b0 >= j * L && b0 + sp <= (j + 1) * L) { ps = min(ps, 2 * q); pe = max(pe, 2 * q + 1); }
+            if (b0 + sp >= j * L && e0 <= (j + 1) * L) { ps = min(ps, 2 * q + 1); pe = max(pe, 2 * q + 2); }
+        }
+    }
+    if (pe <= ps) { ps = 0; pe = 0; }
+    return make_int4(c, split, ps, pe);
+}
+
+template <class Acc>
+__device__ __forceinline__ void time_features_chunked(Acc D, int w, const b200aa_clip_norm &nm, int4 tl, float *parts,
+                                                      float *fv, int lane)
+{
+    const float a = nm.a, bp = nm.bp, lo = nm.lo, hi = nm.hi;
+    const int c = tl.x, k0 = lane * c, end = min(w, k0 + c);
+    float plo = 0.f, phi = 0.f, fl = 0.f;
+    float sprev = (k0 > 0 && k0 < w) ? sign_class(D(k0 - 1), lo, hi) : 0.f;
+    for (int n = k0; n < end; ++n) {
+        const float d = D(n);
+        const float y = fmaf(a, d, bp);
+        const float sq = y * y;
+        if (n - k0 < tl.y) plo += sq; else phi += sq;
+        const float sg = sign_class(d, lo, hi);
+        if (n > 0) fl += fabsf(sg - sprev);
+        sprev = sg;
+    }
+    parts[2 * lane] = plo;
+    parts[2 * lane + 1] = phi;
+    __syncwarp();
+    const float tot = warp_sum(plo + phi);
+    fl = warp_sum(fl);
+    float e = 0.f;
+    for (int q = tl.z; q < tl.w; ++q) e += parts[q];
+    float H = 0.f;
+    if (lane < 10) {
+        const float sj = e / (tot + B200AA_EPS);
+        H = -sj * log2f(sj + B200AA_EPS);
+    }
+    H = warp_sum(H);
+    if (lane == 0) {
+        fv[0] = fl * 0.5f / float(w - 1);
+        fv[1] = tot / float(w);
+        fv[2] = H;
+    }
+    __syncwarp();
+}
+
 }  // namespace b200aa

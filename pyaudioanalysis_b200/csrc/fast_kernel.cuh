@@ -343,8 +343,6 @@ __device__ __forceinline__ void flat_dct(const float *ms, int ng, const SmallTab
 // Frames are whole numbers of runs (N % 80 == 0, step % 8 == 0), so zcr / energy / block energies of
 // a frame are sums over its 100 runs and the 50 % overlap is computed once.
 // ----------------------------------------------------------------------------------------------
-// sign(x - mean) in {-1, 0, +1} as a float, from the exact thresholds of b200aa_clip_norm
-__device__ __forceinline__ float sign_class(float d, float lo, float hi) { return (d > lo ? 1.f : 0.f) - (d < hi ? 1.f : 0.f); }
 
 __device__ __forceinline__ void stage_run(const void *clip, int dtype, bool vec_ok, int64_t n0, const b200aa_clip_norm &nm,
                                           float *dst, float *runE, int *runF)
@@ -497,6 +495,7 @@ struct alignas(16) FastFixed {
     float chr[G * 12];                    // raw chroma sums
     float parts[G * 64];                  // entropy parts per warp
     alignas(16) int dlane[32 * 4];        // per-lane constants of the dense pass
+    alignas(16) int4 tlane[32];           // per-lane constants of the chunked time-domain pass (non-run kernels)
     unsigned int next_item;
     alignas(8) unsigned long long mbar;   // completion barrier of the TMA prefetch
 };
@@ -555,6 +554,7 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
     for (int i = tid; i < Nc / 2 + 1; i += NT) s_twp[i] = g_twp[i];
     __syncthreads();
     const SmallTables tb = bind_tables(blob_s, p.bl);
+    if (tid < 32) sm.tlane[tid] = time_lane_init(N, tid);
     if (tid < 16) {
         const DenseLane d0_ = dense_lane_init_h<K>(tid);
         sm.dlane[tid * 4 + 0] = d0_.split; sm.dlane[tid * 4 + 1] = d0_.ps; sm.dlane[tid * 4 + 2] = d0_.pe;
@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
                     int ru = fbase + 1 + f;
                     if (ru > G) ru -= G + 1;
                     const float *frs = sS + f * step;
-                    time_features([&](int n) { return frs[n]; }, N, nm, fvrows + ru * kFvStride, lane);
+                    time_features_chunked([&](int n) { return frs[n]; }, N, nm, sm.tlane[lane], parts + warp * 64, fvrows + ru * kFvStride, lane);
                 }
             }
             // ---- TMA: fetch the next step's new samples (same work item) while this step computes

@@ -16,6 +16,7 @@ inline size_t generic_smem_bytes(int G, int Nc, int Kp, int blob_words)
     b += size_t(G + 1) * kFvStride * sizeof(float);          // feature rows (+ previous frame)
     b += size_t(kWarps) * B200AA_N_MEL * sizeof(float);      // mel scratch
     b += size_t(G + 1) * sizeof(float);                      // row sums
+    b += size_t(kWarps) * 64 * sizeof(float) + 32 * sizeof(int4) + 16;   // time-domain parts + lane constants
     b += size_t(blob_words) * sizeof(int);
     return (b + 15) & ~size_t(15);
 }
@@ -57,10 +58,13 @@ __global__ void __launch_bounds__(kThreads, 2) st_generic_kernel(const StParams 
     float *fvrows = Xrows + size_t(G + 1) * Kp;                          // row 0 = previous frame
     float *mscr = fvrows + size_t(G + 1) * kFvStride;
     float *rowsum = mscr + kWarps * B200AA_N_MEL;
-    int *blob_s = reinterpret_cast<int *>(rowsum + (G + 1));
+    float *tparts = rowsum + ((G + 1 + 3) & ~3);
+    int4 *tlane = reinterpret_cast<int4 *>(tparts + kWarps * 64);
+    int *blob_s = reinterpret_cast<int *>(tlane + 32);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < p.bl.words; i += kThreads) blob_s[i] = p.blob[i];
+    if (tid < 32) tlane[tid] = time_lane_init(p.fft_n, tid);
     __syncthreads();
     const SmallTables tb = bind_tables(blob_s, p.bl);
 
@@ -111,9 +115,10 @@ __global__ void __launch_bounds__(kThreads, 2) st_generic_kernel(const StParams 
                     const float d0 = rd(origin + (g0 + f) * p.step);
                     float *fv = fvrows + size_t(f + 1) * kFvStride;
                     if (p.packed)
-                        time_features([&](int n) { const float2 q = zf[n >> 1]; return ((n & 1) ? q.y : q.x) + d0; }, w, nm, fv, lane);
+                        time_features_chunked([&](int n) { const float2 q = zf[n >> 1]; return ((n & 1) ? q.y : q.x) + d0; }, w, nm,
+                                              tlane[lane], tparts + warp * 64, fv, lane);
                     else
-                        time_features([&](int n) { return zf[n].x + d0; }, w, nm, fv, lane);
+                        time_features_chunked([&](int n) { return zf[n].x + d0; }, w, nm, tlane[lane], tparts + warp * 64, fv, lane);
                 }
                 // no barrier needed before the passes: they only read bufA as well
             }
