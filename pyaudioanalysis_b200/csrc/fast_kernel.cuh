@@ -1,5 +1,5 @@
-// Register-tiled short-term kernel for even windows N = 2*R*R (R = 20 -> 800 samples = 50 ms @ 16 kHz,
-// R = 21 -> 882 samples = 20 ms @ 44.1 kHz).
+// Register-tiled short-term kernel for even windows N = 2*R1*R2 (20x20 -> 800 samples = 50 ms @ 16 kHz,
+// 21x21 -> 882 = 20 ms @ 44.1 kHz, 20x10 -> 400, 20x12 -> 480, 20x15 -> 600).
 //
 // The real frame is packed into R*R complex points z[n] = x[2n] + i x[2n+1] and transformed as an
 // R x R two-pass FFT: every pass is one R-point FFT per thread held entirely in registers
@@ -24,6 +24,9 @@ namespace b200aa {
 #endif
 
 template <int R> struct RFactors;
+template <> struct RFactors<10> { static constexpr int A = 2, B = 5; };
+template <> struct RFactors<12> { static constexpr int A = 4, B = 3; };
+template <> struct RFactors<15> { static constexpr int A = 3, B = 5; };
 template <> struct RFactors<20> { static constexpr int A = 4, B = 5; };
 template <> struct RFactors<21> { static constexpr int A = 3, B = 7; };
 
@@ -472,22 +475,26 @@ struct FastTables {
 };
 
 
-template <int R, int G>
+// Nc = R1 * R2 complex points per frame: n = R2*n1 + n2, k = k1 + R1*k2.  Pass 1: R2 threads per frame, each an
+// R1-point FFT over n1; pass 2 / post-processing: R1 threads per frame, each an R2-point FFT over n2.
+template <int R1, int R2, int G>
 struct FastShape {
-    static constexpr int Nc = R * R, N = 2 * Nc, K = Nc, Kp = DenseShape<Nc>::Kp;   // rows zero-padded to 32*C bins
-    static constexpr int ES = R | 1;             // padded row stride of the transpose buffer (float2)
-    static constexpr int H = R / 2;              // second-pass outputs k2 >= H are published for the partners
-    static constexpr int ZS = Nc - R * H;        // published values per frame
-    static constexpr int FftThreads = G * R;
+    static constexpr int Nc = R1 * R2, N = 2 * Nc, K = Nc, Kp = DenseShape<Nc>::Kp;   // rows zero-padded to 32*C bins
+    static constexpr int TPF = R1 > R2 ? R1 : R2;   // threads that own a frame during the transform
+    static constexpr int ES = R2 | 1;            // padded row stride of the transpose buffer [R1][ES] (float2)
+    static constexpr int H = R2 / 2;             // second-pass outputs k2 >= H are published for the partners
+    static constexpr int ZS = Nc - R1 * H;       // published values per frame
+    static constexpr int FftThreads = G * TPF;
+    static_assert(TPF <= 32, "one frame's transform threads fit a warp-sized slot");
     static constexpr int NT = 32 * G;            // threads per CTA
 };
 
 // fixed-size part of the CTA's shared memory (compile-time offsets)
-template <int R, int G>
+template <int R1, int R2, int G>
 struct alignas(16) FastFixed {
-    using S = FastShape<R, G>;
-    float2 E[G * R * S::ES];              // transpose buffer [G][R][ES]; the |X| rows alias it
-    float2 tw[R * R];                     // W_Nc^(k1 n2)  [k1][n2]
+    using S = FastShape<R1, R2, G>;
+    float2 E[G * R1 * S::ES];              // transpose buffer [G][R][ES]; the |X| rows alias it
+    float2 tw[R1 * R2];                   // W_Nc^(k1 n2)  [k1][n2]
     float2 twp[(S::Nc / 2 + 2) & ~1];     // W_N^k
     alignas(16) float Xprev[2 * S::Kp];   // |X| of the previous step's last frame (double-buffered)
     float fvrows[(G + 1) * kFvStride];    // ring of feature rows: 34 features + the row's sum(X) in slot 34
@@ -500,32 +507,32 @@ struct alignas(16) FastFixed {
     alignas(8) unsigned long long mbar;   // completion barrier of the TMA prefetch
 };
 
-template <int R, int G>
-inline size_t fast_fixed_bytes() { return sizeof(FastFixed<R, G>); }
-template <int R, int G>
+template <int R1, int R2, int G>
+inline size_t fast_fixed_bytes() { return sizeof(FastFixed<R1, R2, G>); }
+template <int R1, int R2, int G>
 inline size_t fast_smem_bytes(int step, int blob_words, bool runs)
 {
-    using S = FastShape<R, G>;
+    using S = FastShape<R1, R2, G>;
     const size_t span_max = size_t(G - 1) * step + S::N;
     const size_t nrun = (span_max / 8 + 4) & ~size_t(3);
     // see the kernel: with run staging the carried tail must survive, otherwise the whole span is dead after pass 1
     const bool zs_alias = runs ? size_t(G) * step >= 2 * size_t(G) * S::ZS : span_max >= 2 * size_t(G) * S::ZS;
-    return fast_fixed_bytes<R, G>() + sizeof(int) * ((blob_words + 3) & ~3) + 2 * sizeof(float) * nrun +
+    return fast_fixed_bytes<R1, R2, G>() + sizeof(int) * ((blob_words + 3) & ~3) + 2 * sizeof(float) * nrun +
            sizeof(float) * (span_max + 8) + (zs_alias ? 0 : sizeof(float2) * G * S::ZS) +
            (runs ? sizeof(short) * (size_t(G) * step + 16) : 0);
 }
 
-template <int R, int G, bool STEP_EVEN, bool RUNS, int MODE>
+template <int R1, int R2, int G, bool STEP_EVEN, bool RUNS, int MODE>
 __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(const StParams p, const float2 *__restrict__ g_tw,
                                                                 const float2 *__restrict__ g_twp, unsigned int *work_counter)
 {
-    using S = FastShape<R, G>;
-    constexpr int Nc = S::Nc, N = S::N, K = S::K, Kp = S::Kp, ES = S::ES, H = S::H, ZS = S::ZS, NT = S::NT;
+    using S = FastShape<R1, R2, G>;
+    constexpr int Nc = S::Nc, N = S::N, K = S::K, Kp = S::Kp, ES = S::ES, H = S::H, ZS = S::ZS, NT = S::NT, TPF = S::TPF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int step = p.step;
     // shared-memory layout: all fixed-size arrays sit at compile-time offsets (no address arithmetic to keep
     // live in registers); the three arrays whose size depends on the hop come last
-    using Fixed = FastFixed<R, G>;
+    using Fixed = FastFixed<R1, R2, G>;
     Fixed &sm = *reinterpret_cast<Fixed *>(smem_raw);
     float2 *const E = sm.E, *const s_tw = sm.tw, *const s_twp = sm.twp;
     float *const Xprev = sm.Xprev, *const fvrows = sm.fvrows, *const mscr = sm.mscr, *const chr = sm.chr;
@@ -545,12 +552,12 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
     // raw int16 landing zone of the TMA prefetch (RUNS only): 8 predecessor samples + G*step new samples
     short *const raw = reinterpret_cast<short *>(sS + (((G - 1) * step + N + 8) & ~3) + (zs_alias ? 0 : 2 * G * ZS));
     float *Xrows = reinterpret_cast<float *>(E);                             // rows f -> Xrows + f*Kp (aliases E)
-    static_assert(size_t(G) * Kp * sizeof(float) <= size_t(G) * R * ES * sizeof(float2), "alias");
+    static_assert(size_t(G) * Kp * sizeof(float) <= size_t(G) * R1 * ES * sizeof(float2), "alias");
     static_assert((G & (G - 1)) == 0 && G * 26 <= NT, "tile mapping");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < p.bl.words; i += NT) blob_s[i] = p.blob[i];
-    for (int i = tid; i < R * R; i += NT) s_tw[i] = g_tw[i];
+    for (int i = tid; i < R1 * R2; i += NT) s_tw[i] = g_tw[i];
     for (int i = tid; i < Nc / 2 + 1; i += NT) s_twp[i] = g_twp[i];
     __syncthreads();
     const SmallTables tb = bind_tables(blob_s, p.bl);
@@ -564,7 +571,7 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
     unsigned tma_phase = 0;       // parity of the next completion to wait for
     __syncthreads();
     const bool fft_thread = tid < S::FftThreads;
-    const int ff = tid / R, fj = tid - ff * R;          // frame slot / index within the frame's R threads
+    const int ff = tid / TPF, fj = tid - ff * TPF;      // frame slot / index within the frame's TPF threads
 
     // work items are handed out dynamically (one atomic per item) so the tail of the launch is one item long
     for (int64_t item = blockIdx.x; item < p.n_items;) {
@@ -664,45 +671,45 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
 
             // ---- pass 1: thread (frame ff, column n2 = fj): FFT over n1 of z[R*n1 + n2], twiddle, transpose
             float d0 = 0.f;                 // first sample of the frame (kept for the DC bin)
-            if (fft_thread && ff < ng) {
+            if (fft_thread && ff < ng && fj < R2) {
                 const float *fr = sS + ff * step;
                 d0 = fr[0];
-                float2 v[R];
+                float2 v1[R1];
 #pragma unroll
-                for (int n1 = 0; n1 < R; ++n1) {
+                for (int n1 = 0; n1 < R1; ++n1) {
                     float2 z;
-                    if (STEP_EVEN) z = *reinterpret_cast<const float2 *>(fr + 2 * (R * n1 + fj));
-                    else { z.x = fr[2 * (R * n1 + fj)]; z.y = fr[2 * (R * n1 + fj) + 1]; }
-                    v[n1] = make_float2(z.x - d0, z.y - d0);
+                    if (STEP_EVEN) z = *reinterpret_cast<const float2 *>(fr + 2 * (R2 * n1 + fj));
+                    else { z.x = fr[2 * (R2 * n1 + fj)]; z.y = fr[2 * (R2 * n1 + fj) + 1]; }
+                    v1[n1] = make_float2(z.x - d0, z.y - d0);
                 }
-                fft_r<R>(v);
-                float2 *Ef = E + size_t(ff) * R * ES;
+                fft_r<R1>(v1);
+                float2 *Ef = E + size_t(ff) * R1 * ES;
 #pragma unroll
-                for (int k1 = 0; k1 < R; ++k1) {
-                    const float2 w = k1 == 0 ? make_float2(1.f, 0.f) : s_tw[k1 * R + fj];
-                    Ef[k1 * ES + fj] = k1 == 0 ? v[0] : cmul(v[k1], w);
+                for (int k1 = 0; k1 < R1; ++k1) {
+                    const float2 w = k1 == 0 ? make_float2(1.f, 0.f) : s_tw[k1 * R2 + fj];
+                    Ef[k1 * ES + fj] = k1 == 0 ? v1[0] : cmul(v1[k1], w);
                 }
             }
             __syncthreads();
             // ---- pass 2: thread (frame ff, row k1 = fj): FFT over n2 -> Z[k1 + R*k2]
-            float2 v[R];
-            if (fft_thread && ff < ng) {
-                const float2 *Ef = E + size_t(ff) * R * ES + fj * ES;
+            float2 v[R2];
+            if (fft_thread && ff < ng && fj < R1) {
+                const float2 *Ef = E + size_t(ff) * R1 * ES + fj * ES;
 #pragma unroll
-                for (int n2 = 0; n2 < R; ++n2) v[n2] = Ef[n2];
-                fft_r<R>(v);
+                for (int n2 = 0; n2 < R2; ++n2) v[n2] = Ef[n2];
+                fft_r<R2>(v);
                 float2 *Zf = Zs + size_t(ff) * ZS;
 #pragma unroll
-                for (int k2 = H; k2 < R; ++k2) Zf[fj + R * (k2 - H)] = v[k2];
+                for (int k2 = H; k2 < R2; ++k2) Zf[fj + R1 * (k2 - H)] = v[k2];
             }
             __syncthreads();    // all E reads done (|X| rows alias E) and partner values visible
             // ---- post-process: X[k] = ev + W_N^k od, X[Nc-k] = conj(ev - W_N^k od) from (Z[k], Z[Nc-k])
-            if (fft_thread && ff < ng) {
+            if (fft_thread && ff < ng && fj < R1) {
                 const float2 *Zf = Zs + size_t(ff) * ZS;
                 float *Xf = Xrows + size_t(ff) * Kp;
                 const float sc = nm.a / float(2 * K);
                 auto pair = [&](int k, float2 zk, bool do_mirror) {
-                    const float2 zp = Zf[(Nc - k) - R * H];
+                    const float2 zp = Zf[(Nc - k) - R1 * H];
                     const float2 ev = make_float2(zk.x + zp.x, zk.y - zp.y);
                     const float2 od = make_float2(zk.y + zp.y, zp.x - zk.x);
                     const float2 t = cmul(od, s_twp[k]);
@@ -713,7 +720,7 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
                 };
 #pragma unroll
                 for (int k2 = 0; k2 < H; ++k2) {
-                    const int k = fj + R * k2;
+                    const int k = fj + R1 * k2;
                     if (k2 == 0 && fj == 0) {
                         // DC: a * sum(d - d0) + N * (a*d0 + bp)
                         Xf[0] = fabsf(fmaf(nm.a, v[0].x + v[0].y, float(N) * fmaf(nm.a, d0, nm.bp))) / float(K);
@@ -722,7 +729,7 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
                     }
                 }
                 {   // middle index k2 = H: only the lower partner of each pair computes it
-                    const int k = fj + R * H;
+                    const int k = fj + R1 * H;
                     if (2 * k < Nc) pair(k, v[H], true);
                     else if (2 * k == Nc) {          // self-paired bin Nc/2 (R even, thread 0): |X| = |Z|
                         Xf[k] = fsqrt_pos(fmaf(v[H].x, v[H].x, v[H].y * v[H].y)) * (2.f * sc);
@@ -822,11 +829,17 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
 // ----------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------
-inline int fast_r_for_window(int window)
+// window -> (R1, R2) of the register-tiled transform (window = 2 * R1 * R2); 0 = use the generic kernel
+inline bool fast_shape_for_window(int window, int *r1, int *r2)
 {
-    if (window == 800) return 20;
-    if (window == 882) return 21;
-    return 0;
+    switch (window) {
+    case 800: *r1 = 20; *r2 = 20; return true;     // 50 ms @ 16 kHz
+    case 882: *r1 = 21; *r2 = 21; return true;     // 20 ms @ 44.1 kHz
+    case 400: *r1 = 20; *r2 = 10; return true;     // 50 ms @ 8 kHz, 25 ms @ 16 kHz
+    case 480: *r1 = 20; *r2 = 12; return true;     // 30 ms @ 16 kHz, 10 ms @ 48 kHz
+    case 600: *r1 = 20; *r2 = 15; return true;     // 75 ms @ 8 kHz
+    default: return false;
+    }
 }
 
 inline int fast_plan_init(int fs, int window, int step, const std::vector<int> &blob, const BlobLayout &bl,
@@ -834,15 +847,15 @@ inline int fast_plan_init(int fs, int window, int step, const std::vector<int> &
 {
     (void)fs; (void)step; (void)blob; (void)bl;
     *kind = 0;
-    const int R = fast_r_for_window(window);
-    if (!R) return B200AA_OK;
-    const int Nc = R * R, N = 2 * Nc;
+    int R1 = 0, R2 = 0;
+    if (!fast_shape_for_window(window, &R1, &R2)) return B200AA_OK;
+    const int Nc = R1 * R2, N = 2 * Nc;
     const double pi = 3.14159265358979323846264338327950288;
-    std::vector<float2> tw(size_t(R) * R), twp(Nc / 2 + 1);
-    for (int k1 = 0; k1 < R; ++k1)
-        for (int n2 = 0; n2 < R; ++n2) {
+    std::vector<float2> tw(size_t(R1) * R2), twp(Nc / 2 + 1);
+    for (int k1 = 0; k1 < R1; ++k1)
+        for (int n2 = 0; n2 < R2; ++n2) {
             const double a = -2.0 * pi * double((k1 * n2) % Nc) / double(Nc);
-            tw[size_t(k1) * R + n2] = make_float2(float(std::cos(a)), float(std::sin(a)));
+            tw[size_t(k1) * R2 + n2] = make_float2(float(std::cos(a)), float(std::sin(a)));
         }
     for (int k = 0; k <= Nc / 2; ++k) {
         const double a = -2.0 * pi * double(k) / double(N);
@@ -853,18 +866,18 @@ inline int fast_plan_init(int fs, int window, int step, const std::vector<int> &
     if (cudaMemcpy(ft->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) return B200AA_ERR_CUDA;
     if (cudaMemcpy(ft->d_twp, twp.data(), twp.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) return B200AA_ERR_CUDA;
     if (cudaMalloc(&ft->d_counters, 64 * sizeof(unsigned int)) != cudaSuccess) return B200AA_ERR_CUDA;
-    ft->R = R;
-    *kind = R;
+    ft->R = R1 * 100 + R2;
+    *kind = ft->R;
     return B200AA_OK;
 }
 
-template <int R, int G, bool EVEN, bool RUNS, int MODE>
+template <int R1, int R2, int G, bool EVEN, bool RUNS, int MODE>
 inline int fast_launch_t(const FastTables &ft, StParams p, int sm_count, int64_t T, cudaStream_t st)
 {
     constexpr int NT = 32 * G;
-    const size_t smem = fast_smem_bytes<R, G>(p.step, p.bl.words, RUNS);
+    const size_t smem = fast_smem_bytes<R1, R2, G>(p.step, p.bl.words, RUNS);
     if (smem > 110u * 1024u) return B200AA_ERR_UNSUPPORTED;      // very large hop: leave it to the generic kernel
-    auto kern = st_fast_kernel<R, G, EVEN, RUNS, MODE>;
+    auto kern = st_fast_kernel<R1, R2, G, EVEN, RUNS, MODE>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200AA_ERR_CUDA;
     int occ = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem) != cudaSuccess) return B200AA_ERR_CUDA;
@@ -885,32 +898,40 @@ inline int fast_launch_t(const FastTables &ft, StParams p, int sm_count, int64_t
     p.n_items = p.segs_per_clip * p.n_clips;
     const int64_t grid = p.n_items < slots ? p.n_items : slots;
     if (getenv("B200AA_DEBUG"))
-        fprintf(stderr, "[b200aa] fast kernel R=%d G=%d runs=%d mode=%d: smem %zu B, %d CTAs/SM, grid %lld, %lld items of %lld frames\n",
-                R, G, int(RUNS), MODE, smem, occ, (long long)grid, (long long)p.n_items, (long long)seg);
+        fprintf(stderr, "[b200aa] fast kernel %dx%d G=%d runs=%d mode=%d: smem %zu B, %d CTAs/SM, grid %lld, %lld items of %lld frames\n",
+                R1, R2, G, int(RUNS), MODE, smem, occ, (long long)grid, (long long)p.n_items, (long long)seg);
     unsigned int *ctr = ft.d_counters + (ft.next_counter++ % 64u);
     if (cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st) != cudaSuccess) return B200AA_ERR_CUDA;
     kern<<<(unsigned)grid, NT, smem, st>>>(p, ft.d_tw, ft.d_twp, ctr);
     return cudaGetLastError() == cudaSuccess ? B200AA_OK : B200AA_ERR_CUDA;
 }
 
+// run staging needs whole 8-sample runs per frame, per entropy block (window % 80 == 0) and per hop
+template <int R1, int R2, int MODE>
+inline int fast_launch_shape(const FastTables &ft, const StParams &p, int sm_count, int64_t T, cudaStream_t st)
+{
+    constexpr int G = B200AA_FAST_G;
+    constexpr int N = 2 * R1 * R2;
+    const bool even = (p.step % 2) == 0 && (p.origin % 2) == 0;
+    if (N % 80 == 0) {
+        const bool runs = (p.step % 8) == 0 && (p.clip_stride % 8) == 0 && (p.origin % 8) == 0;
+        if (runs) return fast_launch_t<R1, R2, G, true, N % 80 == 0, MODE>(ft, p, sm_count, T, st);
+    }
+    return even ? fast_launch_t<R1, R2, G, true, false, MODE>(ft, p, sm_count, T, st)
+                : fast_launch_t<R1, R2, G, false, false, MODE>(ft, p, sm_count, T, st);
+}
+
 template <int MODE>
 inline int fast_launch_mode(int kind, const FastTables &ft, const StParams &p, int sm_count, int64_t T, cudaStream_t st)
 {
-    const bool even = (p.step % 2) == 0;
-    constexpr int G = B200AA_FAST_G;
-    if (kind == 20) {
-        // whole 8-sample runs per frame and per hop: fused staging + time-domain partials
-        const bool runs = (p.step % 8) == 0 && (p.clip_stride % 8) == 0 && (p.origin % 8) == 0;
-        if (runs) return fast_launch_t<20, G, true, true, MODE>(ft, p, sm_count, T, st);
-        return even ? fast_launch_t<20, G, true, false, MODE>(ft, p, sm_count, T, st)
-                    : fast_launch_t<20, G, false, false, MODE>(ft, p, sm_count, T, st);
+    switch (kind) {
+    case 2020: return fast_launch_shape<20, 20, MODE>(ft, p, sm_count, T, st);
+    case 2121: return fast_launch_shape<21, 21, MODE>(ft, p, sm_count, T, st);
+    case 2010: return fast_launch_shape<20, 10, MODE>(ft, p, sm_count, T, st);
+    case 2012: return fast_launch_shape<20, 12, MODE>(ft, p, sm_count, T, st);
+    case 2015: return fast_launch_shape<20, 15, MODE>(ft, p, sm_count, T, st);
+    default: return B200AA_ERR_UNSUPPORTED;
     }
-    if (kind == 21) {
-        const bool e2 = even && (p.origin % 2) == 0;
-        return e2 ? fast_launch_t<21, G, true, false, MODE>(ft, p, sm_count, T, st)
-                  : fast_launch_t<21, G, false, false, MODE>(ft, p, sm_count, T, st);
-    }
-    return B200AA_ERR_UNSUPPORTED;
 }
 
 inline int fast_launch_features(int kind, const FastTables &ft, const StParams &p, int sm_count, int64_t T, cudaStream_t st)

@@ -122,7 +122,9 @@ def test_edges(P, golden_edges):
 # ------------------------------------------------------------------ oracle on seeded inputs
 @pytest.mark.parametrize("fs,w,s,n", [(16000, 800, 400, 48000), (16000, 800, 800, 16000), (16000, 640, 160, 20000),
                                       (44100, 882, 441, 30000), (8000, 400, 200, 12000), (22050, 1102, 551, 30000),
-                                      (48000, 2400, 1200, 60000), (16000, 1024, 512, 20000), (16000, 883, 300, 9000)])
+                                      (48000, 2400, 1200, 60000), (16000, 1024, 512, 20000), (16000, 883, 300, 9000),
+                                      (16000, 400, 160, 20000), (16000, 480, 160, 20000), (8000, 600, 300, 12000),
+                                      (16000, 400, 133, 9000), (16000, 480, 480, 9600)])
 def test_oracle_configs(P, fs, w, s, n):
     x = O.synth_clip(100 + w, n, fs)
     ref, names = O.feature_extraction(x, fs, w, s)
@@ -245,7 +247,8 @@ def test_kernel_kinds_agree(P):
     """Where a specialised kernel exists it must agree with the generic one (and both with the oracle)."""
     import torch
     from pyaudioanalysis_b200._lib import Plan
-    for fs, w, s in [(16000, 800, 400), (44100, 882, 441), (16000, 800, 800), (16000, 800, 200)]:
+    for fs, w, s in [(16000, 800, 400), (44100, 882, 441), (16000, 800, 800), (16000, 800, 200), (8000, 400, 200),
+                     (16000, 400, 160), (16000, 480, 240), (8000, 600, 300)]:
         clips = np.stack([O.synth_clip(40 + i, 24000, fs) for i in range(3)])
         d = torch.from_numpy(clips).cuda()
         pf, pg = Plan(fs, w, s), Plan(fs, w, s)
@@ -263,7 +266,8 @@ def test_row_kernels_agree(P):
     """spectrogram / chromagram through the specialised kernel, the generic kernel and the oracle."""
     import torch
     from pyaudioanalysis_b200._lib import Plan
-    for fs, w, s, n in [(16000, 800, 400, 40000), (44100, 882, 441, 50000), (16000, 800, 800, 24000), (16000, 800, 200, 16400)]:
+    for fs, w, s, n in [(16000, 800, 400, 40000), (44100, 882, 441, 50000), (16000, 800, 800, 24000), (16000, 800, 200, 16400),
+                        (16000, 400, 160, 16000), (8000, 600, 300, 12000)]:
         clips = np.stack([O.synth_clip(60 + i, n, fs) for i in range(3)])
         d = torch.from_numpy(clips).cuda()
         pf, pg = Plan(fs, w, s), Plan(fs, w, s)
