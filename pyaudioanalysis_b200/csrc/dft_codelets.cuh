@@ -139,4 +139,46 @@ __device__ __forceinline__ void fft_pfa(float2 (&v)[RA * RB])
     }
 }
 
+
+// Cooley-Tukey FFT of length RA*RB with compile-time twiddles (needed when the factors are not coprime:
+// 16 = 4 x 4).  n = RB*a + b, k = ka + RA*kb.
+template <int RA, int RB>
+__device__ __forceinline__ void fft_ct(float2 (&v)[RA * RB])
+{
+    constexpr int N = RA * RB;
+    constexpr Trig<N> T = make_trig<N>();
+    float2 U[N];
+#pragma unroll
+    for (int b = 0; b < RB; ++b) {
+        float2 t[RA];
+#pragma unroll
+        for (int a = 0; a < RA; ++a) t[a] = v[RB * a + b];
+        dft_small<RA>(t);
+#pragma unroll
+        for (int ka = 0; ka < RA; ++ka) {
+            const int e = (b * ka) % N;                 // twiddle W_N^(b ka) = cos - i sin
+            float2 r = t[ka];
+            if (e != 0) {
+                if (4 * e == N) r = make_float2(t[ka].y, -t[ka].x);                  // multiply by -i
+                else if (2 * e == N) r = make_float2(-t[ka].x, -t[ka].y);
+                else if (4 * e == 3 * N) r = make_float2(-t[ka].y, t[ka].x);        // multiply by +i
+                else {
+                    const float c = T.c[e], sn = -T.s[e];                            // (c + i sn), sn = -sin
+                    r = make_float2(fmaf(t[ka].x, c, -t[ka].y * sn), fmaf(t[ka].x, sn, t[ka].y * c));
+                }
+            }
+            U[b * RA + ka] = r;
+        }
+    }
+#pragma unroll
+    for (int ka = 0; ka < RA; ++ka) {
+        float2 t[RB];
+#pragma unroll
+        for (int b = 0; b < RB; ++b) t[b] = U[b * RA + ka];
+        dft_small<RB>(t);
+#pragma unroll
+        for (int kb = 0; kb < RB; ++kb) v[ka + RA * kb] = t[kb];
+    }
+}
+
 }  // namespace b200aa

@@ -1,5 +1,5 @@
 // Register-tiled short-term kernel for even windows N = 2*R1*R2 (20x20 -> 800 samples = 50 ms @ 16 kHz,
-// 21x21 -> 882 = 20 ms @ 44.1 kHz, 20x10 -> 400, 20x12 -> 480, 20x15 -> 600).
+// 21x21 -> 882 = 20 ms @ 44.1 kHz, 20x10 -> 400, 20x12 -> 480, 20x15 -> 600, 16x10 -> 320, 20x16 -> 640).
 //
 // The real frame is packed into R*R complex points z[n] = x[2n] + i x[2n+1] and transformed as an
 // R x R two-pass FFT: every pass is one R-point FFT per thread held entirely in registers
@@ -30,8 +30,14 @@ template <> struct RFactors<15> { static constexpr int A = 3, B = 5; };
 template <> struct RFactors<20> { static constexpr int A = 4, B = 5; };
 template <> struct RFactors<21> { static constexpr int A = 3, B = 7; };
 
+template <> struct RFactors<16> { static constexpr int A = 4, B = 4; };
+
 template <int R>
-__device__ __forceinline__ void fft_r(float2 (&v)[R]) { fft_pfa<RFactors<R>::A, RFactors<R>::B>(v); }
+__device__ __forceinline__ void fft_r(float2 (&v)[R])
+{
+    if constexpr (R == 16) fft_ct<4, 4>(v);                                   // factors not coprime: Cooley-Tukey
+    else fft_pfa<RFactors<R>::A, RFactors<R>::B>(v);                          // prime-factor (twiddle-free)
+}
 
 // ----------------------------------------------------------------------------------------------
 // spectral features with a compile-time bin count: every lane keeps its C = odd(ceil(K/32))
@@ -838,6 +844,8 @@ inline bool fast_shape_for_window(int window, int *r1, int *r2)
     case 400: *r1 = 20; *r2 = 10; return true;     // 50 ms @ 8 kHz, 25 ms @ 16 kHz
     case 480: *r1 = 20; *r2 = 12; return true;     // 30 ms @ 16 kHz, 10 ms @ 48 kHz
     case 600: *r1 = 20; *r2 = 15; return true;     // 75 ms @ 8 kHz
+    case 320: *r1 = 16; *r2 = 10; return true;     // 20 ms @ 16 kHz, 40 ms @ 8 kHz
+    case 640: *r1 = 20; *r2 = 16; return true;     // 40 ms @ 16 kHz
     default: return false;
     }
 }
@@ -930,6 +938,8 @@ inline int fast_launch_mode(int kind, const FastTables &ft, const StParams &p, i
     case 2010: return fast_launch_shape<20, 10, MODE>(ft, p, sm_count, T, st);
     case 2012: return fast_launch_shape<20, 12, MODE>(ft, p, sm_count, T, st);
     case 2015: return fast_launch_shape<20, 15, MODE>(ft, p, sm_count, T, st);
+    case 1610: return fast_launch_shape<16, 10, MODE>(ft, p, sm_count, T, st);
+    case 2016: return fast_launch_shape<20, 16, MODE>(ft, p, sm_count, T, st);
     default: return B200AA_ERR_UNSUPPORTED;
     }
 }

@@ -109,11 +109,13 @@ def main():
     pg.force_generic(True)
     msg = timed(lambda: pkg.feature_extraction_batch(cg, 16000, 800, 400, plan=pg), reps=5)
     ms25 = timed(lambda: pkg.feature_extraction_batch(cg, 16000, 400, 160), reps=5)            # 20x10 register-tiled kernel
-    ms40 = timed(lambda: pkg.feature_extraction_batch(cg, 16000, 640, 320), reps=5)            # no specialisation: generic
+    ms40 = timed(lambda: pkg.feature_extraction_batch(cg, 16000, 640, 320), reps=5)            # 20x16 register-tiled kernel
+    ms64 = timed(lambda: pkg.feature_extraction_batch(cg, 16000, 1024, 512), reps=5)           # no specialisation: generic
     emit({"config": "other windows: 1000 x 10 s @16 kHz", "ms_800_400_forced_generic": msg,
           "frames_per_s_800_400_forced_generic": 399000 / (msg * 1e-3), "ms_400_160_fast_20x10": ms25,
-          "frames_per_s_400_160": 1000 * ((160000 - 400) // 160 + 1) / (ms25 * 1e-3), "ms_640_320_generic": ms40,
-          "frames_per_s_640_320": 1000 * ((160000 - 640) // 320 + 1) / (ms40 * 1e-3)})
+          "frames_per_s_400_160": 1000 * ((160000 - 400) // 160 + 1) / (ms25 * 1e-3), "ms_640_320_fast_20x16": ms40,
+          "frames_per_s_640_320": 1000 * ((160000 - 640) // 320 + 1) / (ms40 * 1e-3), "ms_1024_512_generic": ms64,
+          "frames_per_s_1024_512": 1000 * ((160000 - 1024) // 512 + 1) / (ms64 * 1e-3)})
     del cg
 
     # ---- kernel 0 alone on config 2 (HBM-bound)

@@ -18,7 +18,9 @@ pkg.feature_extraction_batch(clips, 16000, 800, 200)                            
 pkg.feature_extraction_batch(clips, 16000, 800, 800)                              # no overlap
 c44 = torch.from_numpy(np.stack([O.synth_clip(9 + i, 30000, 44100) for i in range(3)])).cuda()
 pkg.feature_extraction_batch(c44, 44100, 882, 441)                                # R = 21, odd hop
-pkg.feature_extraction_batch(clips, 16000, 640, 160)                              # generic kernel
+pkg.feature_extraction_batch(clips, 16000, 640, 160)                              # 20x16 (Cooley-Tukey 16-point codelet)
+pkg.feature_extraction_batch(clips, 16000, 320, 160)                              # 16x10
+pkg.feature_extraction_batch(clips, 16000, 1024, 512)                             # generic kernel
 pkg.feature_extraction_batch(clips, 16000, 400, 160)                              # 20x10 rectangular, run staging
 pkg.feature_extraction_batch(clips, 16000, 480, 240)                              # 20x12
 pkg.feature_extraction_batch(clips, 16000, 600, 150)                              # 20x15, no runs

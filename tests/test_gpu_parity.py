@@ -124,7 +124,8 @@ def test_edges(P, golden_edges):
                                       (44100, 882, 441, 30000), (8000, 400, 200, 12000), (22050, 1102, 551, 30000),
                                       (48000, 2400, 1200, 60000), (16000, 1024, 512, 20000), (16000, 883, 300, 9000),
                                       (16000, 400, 160, 20000), (16000, 480, 160, 20000), (8000, 600, 300, 12000),
-                                      (16000, 400, 133, 9000), (16000, 480, 480, 9600)])
+                                      (16000, 400, 133, 9000), (16000, 480, 480, 9600), (16000, 320, 160, 12000),
+                                      (16000, 640, 321, 12000), (8000, 320, 80, 8000)])
 def test_oracle_configs(P, fs, w, s, n):
     x = O.synth_clip(100 + w, n, fs)
     ref, names = O.feature_extraction(x, fs, w, s)
@@ -248,7 +249,7 @@ def test_kernel_kinds_agree(P):
     import torch
     from pyaudioanalysis_b200._lib import Plan
     for fs, w, s in [(16000, 800, 400), (44100, 882, 441), (16000, 800, 800), (16000, 800, 200), (8000, 400, 200),
-                     (16000, 400, 160), (16000, 480, 240), (8000, 600, 300)]:
+                     (16000, 400, 160), (16000, 480, 240), (8000, 600, 300), (16000, 640, 320), (16000, 320, 160)]:
         clips = np.stack([O.synth_clip(40 + i, 24000, fs) for i in range(3)])
         d = torch.from_numpy(clips).cuda()
         pf, pg = Plan(fs, w, s), Plan(fs, w, s)
