@@ -904,6 +904,7 @@ inline int fast_launch_t(const FastTables &ft, StParams p, int sm_count, int64_t
     p.seg_len = seg;
     p.segs_per_clip = (T + seg - 1) / seg;
     p.n_items = p.segs_per_clip * p.n_clips;
+    if (p.n_items >= (int64_t(1) << 31) || T >= (int64_t(1) << 31)) return B200AA_ERR_UNSUPPORTED;   // 32-bit work / frame indices
     const int64_t grid = p.n_items < slots ? p.n_items : slots;
     if (getenv("B200AA_DEBUG"))
         fprintf(stderr, "[b200aa] fast kernel %dx%d G=%d runs=%d mode=%d: smem %zu B, %d CTAs/SM, grid %lld, %lld items of %lld frames\n",
