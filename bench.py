@@ -218,6 +218,7 @@ def run_ours(args, rank, world, local_rank):
             step(i)
         drain()
         e1.record()
+        launches = L.b200aa_launch_count() - launches0          # our kernels launched inside the timed region
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -227,7 +228,6 @@ def run_ours(args, rank, world, local_rank):
         while time.time() < t_end and len(clk.samples) < 8:
             step(collective=False)       # local work only: the iteration count differs between ranks
             torch.cuda.synchronize()
-    launches = L.b200aa_launch_count() - launches0
     ms_total = e0.elapsed_time(e1)
     kernel_ms = sum(a.elapsed_time(b) for a, b in zip(k_start, k_end)) / args.steps
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)

@@ -238,13 +238,21 @@ static int build_blob(int fs, int K, std::vector<int> &blob, BlobLayout &bl, boo
     bl.chr_off = put_i(c_off);
     bl.chr_bin = put_i(c_bin);
     bl.chr_w = put_f(c_w);
-    {   // pair the longest filter with the shortest, 2nd longest with 2nd shortest, ... (balanced tap counts)
+    {
         std::vector<int> order(40);
         for (int i = 0; i < 40; ++i) order[i] = i;
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return m_count[a] < m_count[b]; });
-        std::vector<int> pairs;
-        for (int i = 0; i < 20; ++i) { pairs.push_back(order[39 - i]); pairs.push_back(order[i]); }
-        bl.mel_pairs = put_i(pairs);
+        // 16 groups of <= 3 filters with balanced tap totals (longest-processing-time greedy)
+        std::vector<int> grp(16 * 3, -1), load(16, 0), cntg(16, 0);
+        for (int i = 39; i >= 0; --i) {
+            const int f = order[i];
+            int best = -1;
+            for (int g = 0; g < 16; ++g)
+                if (cntg[g] < 3 && (best < 0 || load[g] < load[best])) best = g;
+            grp[best * 3 + cntg[best]++] = f;
+            load[best] += m_count[f];
+        }
+        bl.mel_grp = put_i(grp);
     }
     while (blob.size() % 4) blob.push_back(0);
     bl.words = (int)blob.size();

@@ -23,7 +23,7 @@ struct BlobLayout {
     int chr_off;     // [13] per pitch class: first entry
     int chr_bin;     // [chr_nnz] source bin
     int chr_w;       // [chr_nnz] weight (float)
-    int mel_pairs;   // [20 x 2] filters paired long-with-short (balanced flat mel phase)
+    int mel_grp;     // [16 x 3] filters in 16 groups of balanced tap count (-1 = empty slot)
     int words;       // total
 };
 

@@ -126,7 +126,7 @@ __device__ __forceinline__ float row_sum_h(const float *X, int l)
 }
 
 template <int K>
-__device__ __forceinline__ void spectral_features_h(const float *X, const float *Xp, float sxp, const float *chroma_raw,
+__device__ __forceinline__ void spectral_features_h(const float *X, const float *Xp, float sxp,
                                                     const int *dlp, float *parts, float *fv, int l, bool active, float *xsave)
 {
     constexpr int C2 = HalfShape<K>::C2, CB = HalfShape<K>::CB;
@@ -210,7 +210,6 @@ __device__ __forceinline__ void spectral_features_h(const float *X, const float 
         const float sj = fdiv(e, sxx + B200AA_EPS);
         ent = -sj * flog2(sj + B200AA_EPS);
     }
-    const float ch = l < 12 ? fdiv(chroma_raw[l], sxx == 0.f ? B200AA_EPS : sxx) : 0.f;
     // four sums in 4 exchanges: lanes 0-3 spread, 4-7 flux, 8-11 rolloff count, 12-15 entropy
     float q4;
     {
@@ -226,16 +225,12 @@ __device__ __forceinline__ void spectral_features_h(const float *X, const float 
         kk += __shfl_xor_sync(0xffffffffu, kk, 1);
         q4 = kk;
     }
-    const float mean = half_sum(ch) * (1.f / 12.f);
-    const float dv = l < 12 ? ch - mean : 0.f;
-    const float var = half_sum(dv * dv) * (1.f / 12.f);
     if (active) {
-        if (l < 12) fv[21 + l] = ch;
         if (l == 0) {
             fv[3] = cen;
             fv[4] = sx > 0.f ? fsqrt_pos(fdiv(q4, sx)) : 0.f;
-            fv[33] = fsqrt_pos(var);
             fv[34] = sx;
+            fv[35] = sxx;                            // sum X^2: the chroma rows are normalised by it later
         }
         if (l == 4) fv[6] = q4;
         if (l == 8) fv[7] = q4 >= float(K) ? 0.f : q4 * invK;
@@ -274,31 +269,32 @@ __device__ __forceinline__ void time_features_runs_h(const float *runE, const in
     }
 }
 
-// ---- flat phase 1 (all 256 threads, 8 frames): threads 0..159 = (frame, mel filter pair) -> log10 mel
-// energies; threads 160..255 = (frame, pitch class) -> raw chroma tap sums.  Filters are paired
-// long-with-short on the host so every thread sees about the same number of taps.
+// ---- mel + raw chroma on the upper half of the CTA (threads NT/2 .. NT-1) while the lower half runs the dense
+// pass: 16 threads per frame, every thread a group of <= 3 filters with balanced tap totals; then 12 threads per
+// frame for the chroma tap sums
 template <int G>
-__device__ __forceinline__ void flat_mel_chroma(const float *Xrows, int Kp, int ng, const SmallTables &tb,
-                                                const int *pair_tab, float *ms, float *chr, int tid)
+__device__ __forceinline__ void upper_mel_chroma(const float *Xrows, int Kp, int ng, const SmallTables &tb, const int *grp_tab,
+                                                 float *ms, float *chr, int t)
 {
-    if (tid < G * 20) {
-        const int f = tid / 20, pr = tid - f * 20;
+    {
+        const int f = t >> 4, sub = t & 15;
         if (f < ng) {
             const float *X = Xrows + size_t(f) * Kp;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int i = pair_tab[2 * pr + h];
-                const int s0 = tb.mel_start[i], cnt = tb.mel_count[i], off = tb.mel_off[i];
-                float acc = 0.f;
+            for (int h = 0; h < 3; ++h) {
+                const int i = grp_tab[3 * sub + h];
+                if (i >= 0) {
+                    const int s0 = tb.mel_start[i], cnt = tb.mel_count[i], off = tb.mel_off[i];
+                    float acc = 0.f;
 #pragma unroll 4
-                for (int t = 0; t < cnt; ++t) acc = fmaf(X[s0 + t], tb.mel_w[off + t], acc);
-
-                ms[f * B200AA_N_MEL + i] = 0.30102999566398120f * flog2(acc + B200AA_EPS);   // log10
+                    for (int q = 0; q < cnt; ++q) acc = fmaf(X[s0 + q], tb.mel_w[off + q], acc);
+                    ms[f * B200AA_N_MEL + i] = 0.30102999566398120f * flog2(acc + B200AA_EPS);   // log10
+                }
             }
         }
-    } else {
-        const int ct = tid - G * 20;
-        const int f = ct / 12, c = ct - f * 12;
+    }
+    if (t < G * 12) {
+        const int f = t / 12, c = t - f * 12;
         if (f < ng) {
             const float *X = Xrows + size_t(f) * Kp;
             const int e0 = tb.chr_off[c], e1 = tb.chr_off[c + 1];
@@ -309,6 +305,20 @@ __device__ __forceinline__ void flat_mel_chroma(const float *Xrows, int Kp, int 
             }
             chr[f * 12 + c] = acc;
         }
+    }
+}
+
+// chroma rows of two frames per warp: normalise the tap sums by sum X^2 (fv[35]) and add their population std
+__device__ __forceinline__ void chroma_finalize_h(const float *chroma_raw, float *fv, int l, bool active)
+{
+    const float sxx = fv[35];
+    const float ch = l < 12 ? fdiv(chroma_raw[l], sxx == 0.f ? B200AA_EPS : sxx) : 0.f;
+    const float mean = half_sum(ch) * (1.f / 12.f);
+    const float dv = l < 12 ? ch - mean : 0.f;
+    const float var = half_sum(dv * dv) * (1.f / 12.f);
+    if (active) {
+        if (l < 12) fv[21 + l] = ch;
+        if (l == 0) fv[33] = fsqrt_pos(var);
     }
 }
 
@@ -770,35 +780,36 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
                 __syncthreads();
                 continue;
             }
-            // ---- flat phase: mel + log10 / raw chroma over all 8 frames, then DCT rows; dense features per warp
-            flat_mel_chroma<G>(Xrows, Kp, ng, tb, blob_s + p.bl.mel_pairs, mscr, chr, tid);
-            __syncthreads();
-            flat_dct<G>(mscr, ng, tb, fvrows, fbase, tid);
-            {
-                // warps 0..G/2-1: spectral rows of frames (2w, 2w+1); warps G/2..G-1: time-domain rows of the same pairs
-                const int half = lane >> 4, l16 = lane & 15;
-                const int wv = warp < G / 2 ? warp : warp - G / 2;
-                const int fq = 2 * wv + half;
-                const bool act = fq < ng;
-                const int f = act ? fq : 0;                         // inactive halves shadow frame 0 (no stores)
+            // ---- phase A: lower half of the CTA = dense spectral rows (two frames per warp); upper half = mel taps +
+            // log10 and the raw chroma sums of all frames
+            const int half = lane >> 4, l16 = lane & 15;
+            const int wv = warp < G / 2 ? warp : warp - G / 2;
+            const int fq = 2 * wv + half;
+            const bool act = fq < ng;
+            const int f = act ? fq : 0;                         // inactive halves shadow frame 0 (no stores)
+            int rr = fbase + 1 + f;
+            if (rr > G) rr -= G + 1;
+            float *fv = fvrows + rr * kFvStride;
+            if (warp >= G / 2) {
+                upper_mel_chroma<G>(Xrows, Kp, ng, tb, blob_s + p.bl.mel_grp, mscr, chr, tid - NT / 2);
+            } else {
                 const fidx_t fr = g0 + f;
-                int rr = fbase + 1 + f;
-                if (rr > G) rr -= G + 1;
-                float *fv = fvrows + rr * kFvStride;
-                if (warp >= G / 2) {
-                    if (RUNS) {
-                        time_features_runs_h<N>(runE + (f * step) / 8, runF + (f * step) / 8, fv, l16, act);
-                    }
-                } else {
-                    const float *X = Xrows + size_t(f) * Kp;
-                    const bool has_prev = (fr > 0) && !(f == 0 && g0 == t0 - halo);
-                    const float *Xp = has_prev ? (f > 0 ? Xrows + size_t(f - 1) * Kp : Xprev + xsel * Kp) : X;
-                    // the neighbour's row sum is produced concurrently by another half-warp: recompute it in the same order
-                    const float rs = row_sum_h<K>(Xp, l16);
-                    const float sxp = (has_prev && f == 0) ? fvrows[fbase * kFvStride + 34] : rs;
-                    spectral_features_h<K>(X, Xp, sxp, chr + f * 12, sm.dlane + l16 * 4, parts + (warp * 2 + half) * 32, fv, l16, act,
-                                           (act && f == ng - 1) ? Xprev + (xsel ^ 1) * Kp : nullptr);
-                }
+                const float *X = Xrows + size_t(f) * Kp;
+                const bool has_prev = (fr > 0) && !(f == 0 && g0 == t0 - halo);
+                const float *Xp = has_prev ? (f > 0 ? Xrows + size_t(f - 1) * Kp : Xprev + xsel * Kp) : X;
+                // the neighbour's row sum is produced concurrently by another half-warp: recompute it in the same order
+                const float rs = row_sum_h<K>(Xp, l16);
+                const float sxp = (has_prev && f == 0) ? fvrows[fbase * kFvStride + 34] : rs;
+                spectral_features_h<K>(X, Xp, sxp, sm.dlane + l16 * 4, parts + (warp * 2 + half) * 32, fv, l16, act,
+                                       (act && f == ng - 1) ? Xprev + (xsel ^ 1) * Kp : nullptr);
+            }
+            __syncthreads();
+            // ---- phase B: DCT rows (all threads), then chroma normalisation (lower half) / time-domain rows (upper half)
+            flat_dct<G>(mscr, ng, tb, fvrows, fbase, tid);
+            if (warp >= G / 2) {
+                if (RUNS) time_features_runs_h<N>(runE + (f * step) / 8, runF + (f * step) / 8, fv, l16, act);
+            } else {
+                chroma_finalize_h(chr + f * 12, fv, l16, act);
             }
             __syncthreads();
             // ---- store the [n_out x 8] tile: 8 consecutive threads -> 8 consecutive frames of one feature row
@@ -897,7 +908,10 @@ inline int fast_launch_t(const FastTables &ft, StParams p, int sm_count, int64_t
     int64_t per_clip = (slots * 8 + p.n_clips - 1) / p.n_clips;
     if (per_clip < 1) per_clip = 1;
     int64_t seg = (T + per_clip - 1) / per_clip;
-    if (seg < 46) seg = 46;
+    // throughput runs keep items >= 46 frames (halo <= 4 %); when the whole launch cannot fill the machine anyway
+    // (a single short clip through the NumPy drop-in) latency wins: one 8-frame CTA step per item
+    const int64_t min_seg = (T * p.n_clips >= 46 * slots) ? 46 : 6;
+    if (seg < min_seg) seg = min_seg;
     seg = ((seg + 2 + G - 1) / G) * G - 2;
     if (const char *ov = getenv("B200AA_SEG")) { const long v = atol(ov); if (v > 0) seg = v; }   // tuning override
     if (seg > T) seg = T;
