@@ -1,12 +1,13 @@
 // Register-tiled short-term kernel for even windows N = 2*R1*R2 (20x20 -> 800 samples = 50 ms @ 16 kHz,
 // 21x21 -> 882 = 20 ms @ 44.1 kHz, 20x10 -> 400, 20x12 -> 480, 20x15 -> 600, 16x10 -> 320, 20x16 -> 640).
 //
-// The real frame is packed into R*R complex points z[n] = x[2n] + i x[2n+1] and transformed as an
-// R x R two-pass FFT: every pass is one R-point FFT per thread held entirely in registers
-// (prime-factor 4x5 / 3x7 butterflies, all twiddles compile-time constants), with one padded
-// shared-memory transpose between the passes.  R threads own a frame; 8 frames per CTA step.
-// Post-processing computes X[k] and X[Nc-k] from one (Z[k], Z[Nc-k]) pair, so only half of the
-// second-pass outputs travel through shared memory.
+// The real frame is packed into Nc = R1*R2 complex points z[n] = x[2n] + i x[2n+1] and transformed as an
+// R1 x R2 two-pass FFT: every pass is one small FFT per thread held entirely in registers (prime-factor
+// 4x5 / 3x7 / 2x5 / 3x4 / 3x5 butterflies without internal twiddles, 4x4 Cooley-Tukey for 16; all
+// constants are immediates, butterflies use the sm_100 FP32x2 instructions), with one padded shared-memory
+// transpose between the passes.  max(R1, R2) threads own a frame; 8 frames per CTA step.  Post-processing
+// computes |X[k]| and |X[Nc-k]| from one (Z[k], Z[Nc-k]) pair, so only half of the second-pass outputs
+// travel through shared memory.  Samples arrive by TMA (cp.async.bulk + mbarrier) one step ahead.
 #pragma once
 #include <cstdio>
 #include <cstdlib>
@@ -17,7 +18,7 @@
 namespace b200aa {
 
 #ifndef B200AA_FAST_G
-#define B200AA_FAST_G 8       // frames per CTA step (CTA = 32*G threads, one warp per frame)
+#define B200AA_FAST_G 8       // frames per CTA step (CTA = 32*G threads)
 #endif
 #ifndef B200AA_FAST_MINBLOCKS
 #define B200AA_FAST_MINBLOCKS 3   // CTAs per SM the fast kernel is compiled for (register budget)
@@ -29,8 +30,7 @@ template <> struct RFactors<12> { static constexpr int A = 4, B = 3; };
 template <> struct RFactors<15> { static constexpr int A = 3, B = 5; };
 template <> struct RFactors<20> { static constexpr int A = 4, B = 5; };
 template <> struct RFactors<21> { static constexpr int A = 3, B = 7; };
-
-template <> struct RFactors<16> { static constexpr int A = 4, B = 4; };
+template <> struct RFactors<16> { static constexpr int A = 4, B = 4; };   // not coprime: Cooley-Tukey
 
 template <int R>
 __device__ __forceinline__ void fft_r(float2 (&v)[R])
@@ -39,11 +39,6 @@ __device__ __forceinline__ void fft_r(float2 (&v)[R])
     else fft_pfa<RFactors<R>::A, RFactors<R>::B>(v);                          // prime-factor (twiddle-free)
 }
 
-// ----------------------------------------------------------------------------------------------
-// spectral features with a compile-time bin count: every lane keeps its C = odd(ceil(K/32))
-// consecutive bins in registers (odd stride => conflict-free loads) and all dense reductions run
-// on those registers.  Same arithmetic as spectral_features() in common.cuh.
-// ----------------------------------------------------------------------------------------------
 // ---- cheap math: MUFU-based reciprocal / rsqrt / log2 (2 ulp); the parity tolerance is 1e-4
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
 // rsqrtf() is the MUFU.RSQ approximation; __frsqrt_rn() is the correctly rounded (slow) one -- measured 12 % slower
@@ -322,7 +317,7 @@ __device__ __forceinline__ void chroma_finalize_h(const float *chroma_raw, float
     }
 }
 
-// ---- flat phase 2: threads 0..207 = (frame, cepstral row c, half h): folded DCT-II
+// ---- DCT: threads 0..207 = (frame, cepstral row c, half h): folded DCT-II
 //   y_c = sum_{n<20} D[c][n] * ((m_n - k) + (-1)^c (m_{39-n} - k)),  k = m_0 (any constant works for
 //   c >= 1 because those rows are orthogonal to constants; row 0 adds it back): keeps the float32 sum
 //   free of the large common offset of the log-mel values.
@@ -685,7 +680,7 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
                 prefetched = true;
             }
 
-            // ---- pass 1: thread (frame ff, column n2 = fj): FFT over n1 of z[R*n1 + n2], twiddle, transpose
+            // ---- pass 1: thread (frame ff, column n2 = fj): R1-point FFT over n1 of z[R2*n1 + n2], twiddle, transpose
             float d0 = 0.f;                 // first sample of the frame (kept for the DC bin)
             if (fft_thread && ff < ng && fj < R2) {
                 const float *fr = sS + ff * step;
@@ -707,7 +702,7 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
                 }
             }
             __syncthreads();
-            // ---- pass 2: thread (frame ff, row k1 = fj): FFT over n2 -> Z[k1 + R*k2]
+            // ---- pass 2: thread (frame ff, row k1 = fj): R2-point FFT over n2 -> Z[k1 + R1*k2]
             float2 v[R2];
             if (fft_thread && ff < ng && fj < R1) {
                 const float2 *Ef = E + size_t(ff) * R1 * ES + fj * ES;
