@@ -9,6 +9,7 @@
 // computes |X[k]| and |X[Nc-k]| from one (Z[k], Z[Nc-k]) pair, so only half of the second-pass outputs
 // travel through shared memory.  Samples arrive by TMA (cp.async.bulk + mbarrier) one step ahead.
 #pragma once
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -470,11 +471,13 @@ __device__ __forceinline__ void stage_run_smem(const short *raw8, bool has_pred,
 // ----------------------------------------------------------------------------------------------
 // kernel
 // ----------------------------------------------------------------------------------------------
+constexpr unsigned int kCounterRing = 1024;   // launches that may be in flight at once on different streams
+
 struct FastTables {
     float2 *d_tw = nullptr;      // [R][R]   W_Nc^(k1*n2) stored [k1][n2]
     float2 *d_twp = nullptr;     // [Nc/2+1] W_N^k
-    unsigned int *d_counters = nullptr;   // ring of work counters (one per in-flight launch)
-    mutable unsigned int next_counter = 0;
+    unsigned int *d_counters = nullptr;   // ring of work counters (one per in-flight launch; zeroed in-stream before use)
+    mutable std::atomic<unsigned int> next_counter{0};
     int R = 0;
     void release()
     {
@@ -879,7 +882,7 @@ inline int fast_plan_init(int fs, int window, int step, const std::vector<int> &
     if (cudaMalloc(&ft->d_twp, twp.size() * sizeof(float2)) != cudaSuccess) return B200AA_ERR_CUDA;
     if (cudaMemcpy(ft->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) return B200AA_ERR_CUDA;
     if (cudaMemcpy(ft->d_twp, twp.data(), twp.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) return B200AA_ERR_CUDA;
-    if (cudaMalloc(&ft->d_counters, 64 * sizeof(unsigned int)) != cudaSuccess) return B200AA_ERR_CUDA;
+    if (cudaMalloc(&ft->d_counters, kCounterRing * sizeof(unsigned int)) != cudaSuccess) return B200AA_ERR_CUDA;
     ft->R = R1 * 100 + R2;
     *kind = ft->R;
     return B200AA_OK;
@@ -918,7 +921,7 @@ inline int fast_launch_t(const FastTables &ft, StParams p, int sm_count, int64_t
     if (getenv("B200AA_DEBUG"))
         fprintf(stderr, "[b200aa] fast kernel %dx%d G=%d runs=%d mode=%d: smem %zu B, %d CTAs/SM, grid %lld, %lld items of %lld frames\n",
                 R1, R2, G, int(RUNS), MODE, smem, occ, (long long)grid, (long long)p.n_items, (long long)seg);
-    unsigned int *ctr = ft.d_counters + (ft.next_counter++ % 64u);
+    unsigned int *ctr = ft.d_counters + (ft.next_counter.fetch_add(1u, std::memory_order_relaxed) % kCounterRing);
     if (cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st) != cudaSuccess) return B200AA_ERR_CUDA;
     kern<<<(unsigned)grid, NT, smem, st>>>(p, ft.d_tw, ft.d_twp, ctr);
     return cudaGetLastError() == cudaSuccess ? B200AA_OK : B200AA_ERR_CUDA;
