@@ -331,10 +331,11 @@ def feature_extraction(signal, fs, window, step, deltas=True):
     window, step = int(window), int(step)
     y = normalize_clip(signal)
     T = frame_count(len(y), window, step)
-    if T == 0:
-        raise ValueError("need at least one array to concatenate")
     K = int(window / 2)
-    chroma_operator(fs, K)  # raises early like the reference would on frame 0
+    mel_filterbank(fs, K)   # :578 -- built before the frame loop: its IndexError (:230-231) comes first
+    if T == 0:
+        raise ValueError("need at least one array to concatenate")          # :684
+    chroma_operator(fs, K)  # raises early like the reference would on frame 0 (:290-294)
     rows = []
     chunk = max(1, (1 << 22) // window)
     Xlast = None

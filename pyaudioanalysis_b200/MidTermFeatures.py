@@ -27,7 +27,7 @@ def mid_feature_extraction(signal, sampling_rate, mid_window, mid_step, short_wi
     plan = get_plan(_fs_int(sampling_rate), w, s)
     T = lib().b200aa_num_frames(x.shape[0], w, s)
     if T <= 0:
-        check(_lib.ERR_TOO_SHORT)
+        ShortTermFeatures._raise_no_frames(plan.fs, w)
     ratio, stepr = mid_ratios(mid_window, mid_step, short_window, short_step)
     if ratio < 1 or stepr < 1:
         raise ValueError("mid-term window / step shorter than one short-term step")

@@ -60,6 +60,13 @@ def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
+def _raise_no_frames(fs, window):
+    """A clip shorter than one window: the reference has already built the mel bank (IndexError when it cannot,
+    ShortTermFeatures.py:578 / :230-231) when np.concatenate finds no frames (ValueError, :684)."""
+    _lib.host_table(fs, window, "mel")
+    check(_lib.ERR_TOO_SHORT)
+
+
 def feature_extraction(signal, sampling_rate, window, step, deltas=True):
     """Short-term features, reference ShortTermFeatures.py:543-685.
 
@@ -72,7 +79,7 @@ def feature_extraction(signal, sampling_rate, window, step, deltas=True):
     plan = get_plan(_fs_int(sampling_rate), window, step)
     T = lib().b200aa_num_frames(x.shape[0], window, step)
     if T <= 0:
-        check(_lib.ERR_TOO_SHORT)
+        _raise_no_frames(plan.fs, window)
     F = 68 if deltas else 34
     out = np.empty((F, T), dtype=np.float32)
     check(lib().b200aa_st_features_host(plan.handle, _ptr(x), code, 1, x.shape[0], 1 if deltas else 0, _ptr(out)))

@@ -129,6 +129,7 @@ struct b200aa_plan {
     int device = 0, sm_count = 0;
     int force_generic = 0;
     int fast_kind = 0;                  // 0 = none, else index of the specialised kernel
+    int tables_status = B200AA_OK;      // B200AA_ERR_CHROMA / _MEL_RANGE when the reference cannot build its tables
     BlobLayout bl{};
     int *d_blob = nullptr;
     std::vector<int> h_blob;
@@ -187,15 +188,13 @@ static int get_transform(b200aa_plan *pl, int n, Transform **out)
 }
 
 // pack mel CSR + DCT + chroma entries into one int32 blob
-static int build_blob(int fs, int K, std::vector<int> &blob, BlobLayout &bl, bool need_features)
+// Returns the status of the feature tables (mfcc_filter_banks runs before the frame loop, :578 / :230-231, the chroma
+// scatter fails on frame 0, :290-294); the blob is built either way so that spectrogram() still works.
+static int build_blob(int fs, int K, std::vector<int> &blob, BlobLayout &bl)
 {
     std::vector<double> mel, chr, dct;
     int rc_mel = b200aa_host::build_mel(fs, K, mel);
     int rc_chr = b200aa_host::build_chroma(fs, K, chr);
-    if (need_features) {
-        if (rc_chr != B200AA_OK) return rc_chr;    // the reference fails in chroma_features on frame 0 ...
-        if (rc_mel != B200AA_OK) return rc_mel;    // ... or earlier in mfcc_filter_banks
-    }
     b200aa_host::build_dct(dct);
     std::vector<int> m_start(40, 0), m_count(40, 0), m_off(40, 0);
     std::vector<float> m_w;
@@ -256,7 +255,7 @@ static int build_blob(int fs, int K, std::vector<int> &blob, BlobLayout &bl, boo
     }
     while (blob.size() % 4) blob.push_back(0);
     bl.words = (int)blob.size();
-    return (rc_chr != B200AA_OK) ? rc_chr : rc_mel;
+    return (rc_mel != B200AA_OK) ? rc_mel : rc_chr;
 }
 
 extern "C" int b200aa_plan_create(b200aa_plan **out, int fs, int window, int step)
@@ -270,8 +269,7 @@ extern "C" int b200aa_plan_create(b200aa_plan **out, int fs, int window, int ste
     CK(cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, pl->device));
     // tables that only feature_extraction / chromagram need may be unbuildable (the reference raises
     // there too); spectrogram must still work, so remember the status instead of failing here.
-    int trc = build_blob(fs, pl->K, pl->h_blob, pl->bl, false);
-    (void)trc;
+    pl->tables_status = build_blob(fs, pl->K, pl->h_blob, pl->bl);
     CK(cudaMalloc(&pl->d_blob, sizeof(int) * pl->h_blob.size()));
     CK(cudaMemcpy(pl->d_blob, pl->h_blob.data(), sizeof(int) * pl->h_blob.size(), cudaMemcpyHostToDevice));
     Transform *t = nullptr;
@@ -296,13 +294,12 @@ extern "C" int b200aa_plan_force_generic(b200aa_plan *plan, int on)
     return prev;
 }
 
-// feature tables status (chroma / mel buildable?) -- recomputed cheaply on the host
-static int feature_tables_status(const b200aa_plan *pl)
+// a plan's tables live on the device that was current when it was created
+static int plan_device_check(const b200aa_plan *pl)
 {
-    std::vector<double> t;
-    int rc = b200aa_host::build_chroma(pl->fs, pl->K, t);
-    if (rc != B200AA_OK) return rc;
-    return b200aa_host::build_mel(pl->fs, pl->K, t);
+    int dev = -1;
+    CK(cudaGetDevice(&dev));
+    return dev == pl->device ? B200AA_OK : B200AA_ERR_INVALID;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -620,10 +617,13 @@ extern "C" int b200aa_st_features(const b200aa_plan *plan, const void *d_sig, in
     if (!plan || !d_sig || !d_norm || !d_out || n_clips < 0 || (dtype != 0 && dtype != 1) || clip_stride < n_samples)
         return B200AA_ERR_INVALID;
     b200aa_plan *pl = const_cast<b200aa_plan *>(plan);
-    int rc = feature_tables_status(pl);
-    if (rc != B200AA_OK) return rc;
+    // error order of the reference: mel bank (before the loop), no frames (:684), chroma (frame 0)
+    if (pl->tables_status == B200AA_ERR_MEL_RANGE) return B200AA_ERR_MEL_RANGE;
     const int64_t T = b200aa_host::num_frames(n_samples, pl->window, pl->step);
     if (T == 0) return B200AA_ERR_TOO_SHORT;
+    int rc = pl->tables_status;
+    if (rc != B200AA_OK) return rc;
+    if ((rc = plan_device_check(pl)) != B200AA_OK) return rc;
     if (t_stride < T) return B200AA_ERR_INVALID;
     if (n_clips == 0) return B200AA_OK;
     Transform *t = nullptr;
@@ -652,8 +652,10 @@ extern "C" int b200aa_spectrogram(const b200aa_plan *plan, const void *d_sig, in
     const int64_t R = b200aa_spectrogram_rows(n_samples, w, s);
     if (R <= 0) return B200AA_ERR_TOO_SHORT;      // np.zeros with a non-positive row count / empty result
     if (n_clips == 0) return B200AA_OK;
+    int rc = plan_device_check(pl);
+    if (rc != B200AA_OK) return rc;
     Transform *t = nullptr;
-    int rc = get_transform(pl, w, &t);
+    rc = get_transform(pl, w, &t);
     if (rc != B200AA_OK) return rc;
     StParams p;
     fill_common(p, pl, t, d_sig, dtype, n_clips, n_samples, clip_stride, nullptr, d_norm, d_out);
@@ -678,9 +680,10 @@ extern "C" int b200aa_chromagram(const b200aa_plan *plan, const void *d_sig, int
     const int w = pl->window, s = pl->step;
     const int64_t R = b200aa_chromagram_rows(n_samples, w, s);
     if (R <= 0 || n_samples - s - w < 0) return B200AA_ERR_TOO_SHORT;
-    int rc = feature_tables_status(pl);
+    int rc = pl->tables_status;
     if (rc == B200AA_ERR_CHROMA) return rc;
     if (n_clips == 0) return B200AA_OK;
+    if ((rc = plan_device_check(pl)) != B200AA_OK) return rc;
     const int64_t n_it = std::min<int64_t>(R, b200aa_host::range_len(w, n_samples - s, s));        // :349
     // frames that fit entirely: start p = w + i*s with p + w <= N
     int64_t n_full = 0;
@@ -723,21 +726,50 @@ extern "C" int b200aa_chromagram(const b200aa_plan *plan, const void *d_sig, int
 // ------------------------------------------------------------------------------------------------
 // host-buffer entry points
 // ------------------------------------------------------------------------------------------------
-// slot i of the plan's workspace, grown to at least n bytes (caller holds host_mu)
-struct DevBuf {
-    void *p = nullptr;
-    int alloc_from(b200aa_plan *pl, int slot, size_t n)
+// slot `slot` of the plan's workspace, grown to at least n bytes (caller holds host_mu); nullptr = cudaMalloc failed
+static void *workspace(b200aa_plan *pl, int slot, size_t n)
+{
+    if (pl->ws_cap[slot] < n) {
+        if (pl->ws[slot]) cudaFree(pl->ws[slot]);
+        pl->ws[slot] = nullptr;
+        pl->ws_cap[slot] = 0;
+        const size_t want = n + n / 4 + 4096;
+        if (cudaMalloc(&pl->ws[slot], want) != cudaSuccess) return nullptr;
+        pl->ws_cap[slot] = want;
+    }
+    return pl->ws[slot];
+}
+
+// One host-buffer call: takes the plan's workspace lock, uploads the clips (slot 0) and produces their normalisation
+// records (slot 1); the entry points add their own kernels and downloads on the same (legacy default) stream.
+struct HostCall {
+    b200aa_plan *pl;
+    std::unique_lock<std::mutex> hold;
+    cudaStream_t st = nullptr;
+    void *sig = nullptr;
+    b200aa_clip_norm *norm = nullptr;
+    explicit HostCall(const b200aa_plan *plan) : pl(const_cast<b200aa_plan *>(plan)), hold(pl->host_mu) {}
+    int upload(const void *h_sig, int dtype, int64_t n_clips, int64_t n_samples)
     {
-        if (pl->ws_cap[slot] < n) {
-            if (pl->ws[slot]) cudaFree(pl->ws[slot]);
-            pl->ws[slot] = nullptr;
-            pl->ws_cap[slot] = 0;
-            const size_t want = n + n / 4 + 4096;
-            if (cudaMalloc(&pl->ws[slot], want) != cudaSuccess) return -1;
-            pl->ws_cap[slot] = want;
-        }
-        p = pl->ws[slot];
-        return 0;
+        int rc = plan_device_check(pl);
+        if (rc != B200AA_OK) return rc;
+        const size_t in_b = size_t(n_clips) * n_samples * (dtype == B200AA_DTYPE_I16 ? 2 : 4);
+        sig = workspace(pl, 0, in_b);
+        norm = static_cast<b200aa_clip_norm *>(workspace(pl, 1, sizeof(b200aa_clip_norm) * n_clips));
+        if (!sig || !norm) return cuda_fail(cudaGetLastError(), "cudaMalloc");
+        CK(cudaMemcpyAsync(sig, h_sig, in_b, cudaMemcpyHostToDevice, st));
+        return b200aa_clip_stats(sig, dtype, n_clips, n_samples, n_samples, nullptr, norm, st);
+    }
+    float *result(int slot, size_t bytes) { return static_cast<float *>(workspace(pl, slot, bytes)); }
+    int download(void *h_dst, const void *d_src, size_t bytes)
+    {
+        CK(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
+        return B200AA_OK;
+    }
+    int finish()
+    {
+        CK(cudaStreamSynchronize(st));
+        return B200AA_OK;
     }
 };
 
@@ -745,25 +777,20 @@ extern "C" int b200aa_st_features_host(const b200aa_plan *plan, const void *h_si
                                        int64_t n_samples, int deltas, float *h_out)
 {
     if (!plan || !h_sig || !h_out || n_clips < 1 || (dtype != 0 && dtype != 1)) return B200AA_ERR_INVALID;
+    if (plan->tables_status == B200AA_ERR_MEL_RANGE) return B200AA_ERR_MEL_RANGE;
     const int64_t T = b200aa_host::num_frames(n_samples, plan->window, plan->step);
     if (T == 0) return B200AA_ERR_TOO_SHORT;
-    const int F = deltas ? 68 : 34;
-    const size_t in_b = size_t(n_clips) * n_samples * (dtype == 0 ? 2 : 4), out_b = size_t(n_clips) * F * T * 4;
-    b200aa_plan *pl = const_cast<b200aa_plan *>(plan);
-    std::lock_guard<std::mutex> hold(pl->host_mu);
-    DevBuf sig, nm, out;
-    if (sig.alloc_from(pl, 0, in_b) || nm.alloc_from(pl, 1, sizeof(b200aa_clip_norm) * n_clips) || out.alloc_from(pl, 2, out_b))
-        return cuda_fail(cudaGetLastError(), "cudaMalloc");
-    cudaStream_t st = nullptr;
-    CK(cudaMemcpyAsync(sig.p, h_sig, in_b, cudaMemcpyHostToDevice, st));
-    int rc = b200aa_clip_stats(sig.p, dtype, n_clips, n_samples, n_samples, nullptr, (b200aa_clip_norm *)nm.p, st);
+    if (plan->tables_status != B200AA_OK) return plan->tables_status;
+    const size_t out_b = size_t(n_clips) * (deltas ? 68 : 34) * T * 4;
+    HostCall hc(plan);
+    int rc = hc.upload(h_sig, dtype, n_clips, n_samples);
     if (rc) return rc;
-    rc = b200aa_st_features(plan, sig.p, dtype, n_clips, n_samples, n_samples, nullptr, (b200aa_clip_norm *)nm.p, deltas,
-                            (float *)out.p, T, st);
+    float *out = hc.result(2, out_b);
+    if (!out) return cuda_fail(cudaGetLastError(), "cudaMalloc");
+    rc = b200aa_st_features(plan, hc.sig, dtype, n_clips, n_samples, n_samples, nullptr, hc.norm, deltas, out, T, hc.st);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(h_out, out.p, out_b, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    return B200AA_OK;
+    if ((rc = hc.download(h_out, out, out_b))) return rc;
+    return hc.finish();
 }
 
 extern "C" int b200aa_spectrogram_host(const b200aa_plan *plan, const void *h_sig, int dtype, int64_t n_samples, float *h_out)
@@ -771,21 +798,16 @@ extern "C" int b200aa_spectrogram_host(const b200aa_plan *plan, const void *h_si
     if (!plan || !h_sig || !h_out || (dtype != 0 && dtype != 1)) return B200AA_ERR_INVALID;
     const int64_t R = b200aa_spectrogram_rows(n_samples, plan->window, plan->step);
     if (R <= 0) return B200AA_ERR_TOO_SHORT;
-    const size_t in_b = size_t(n_samples) * (dtype == 0 ? 2 : 4), out_b = size_t(R) * plan->K * 4;
-    b200aa_plan *pl = const_cast<b200aa_plan *>(plan);
-    std::lock_guard<std::mutex> hold(pl->host_mu);
-    DevBuf sig, nm, out;
-    if (sig.alloc_from(pl, 0, in_b) || nm.alloc_from(pl, 1, sizeof(b200aa_clip_norm)) || out.alloc_from(pl, 2, out_b))
-        return cuda_fail(cudaGetLastError(), "cudaMalloc");
-    cudaStream_t st = nullptr;
-    CK(cudaMemcpyAsync(sig.p, h_sig, in_b, cudaMemcpyHostToDevice, st));
-    int rc = b200aa_clip_stats(sig.p, dtype, 1, n_samples, n_samples, nullptr, (b200aa_clip_norm *)nm.p, st);
+    const size_t out_b = size_t(R) * plan->K * 4;
+    HostCall hc(plan);
+    int rc = hc.upload(h_sig, dtype, 1, n_samples);
     if (rc) return rc;
-    rc = b200aa_spectrogram(plan, sig.p, dtype, 1, n_samples, n_samples, (b200aa_clip_norm *)nm.p, (float *)out.p, st);
+    float *out = hc.result(2, out_b);
+    if (!out) return cuda_fail(cudaGetLastError(), "cudaMalloc");
+    rc = b200aa_spectrogram(plan, hc.sig, dtype, 1, n_samples, n_samples, hc.norm, out, hc.st);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(h_out, out.p, out_b, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    return B200AA_OK;
+    if ((rc = hc.download(h_out, out, out_b))) return rc;
+    return hc.finish();
 }
 
 extern "C" int b200aa_chromagram_host(const b200aa_plan *plan, const void *h_sig, int dtype, int64_t n_samples, float *h_out)
@@ -793,47 +815,39 @@ extern "C" int b200aa_chromagram_host(const b200aa_plan *plan, const void *h_sig
     if (!plan || !h_sig || !h_out || (dtype != 0 && dtype != 1)) return B200AA_ERR_INVALID;
     const int64_t R = b200aa_chromagram_rows(n_samples, plan->window, plan->step);
     if (R <= 0 || n_samples - plan->step - plan->window < 0) return B200AA_ERR_TOO_SHORT;
-    const size_t in_b = size_t(n_samples) * (dtype == 0 ? 2 : 4), out_b = size_t(R) * 12 * 4;
-    b200aa_plan *pl = const_cast<b200aa_plan *>(plan);
-    std::lock_guard<std::mutex> hold(pl->host_mu);
-    DevBuf sig, nm, out;
-    if (sig.alloc_from(pl, 0, in_b) || nm.alloc_from(pl, 1, sizeof(b200aa_clip_norm)) || out.alloc_from(pl, 2, out_b))
-        return cuda_fail(cudaGetLastError(), "cudaMalloc");
-    cudaStream_t st = nullptr;
-    CK(cudaMemcpyAsync(sig.p, h_sig, in_b, cudaMemcpyHostToDevice, st));
-    int rc = b200aa_clip_stats(sig.p, dtype, 1, n_samples, n_samples, nullptr, (b200aa_clip_norm *)nm.p, st);
+    if (plan->tables_status == B200AA_ERR_CHROMA) return B200AA_ERR_CHROMA;
+    const size_t out_b = size_t(R) * 12 * 4;
+    HostCall hc(plan);
+    int rc = hc.upload(h_sig, dtype, 1, n_samples);
     if (rc) return rc;
-    rc = b200aa_chromagram(plan, sig.p, dtype, 1, n_samples, n_samples, (b200aa_clip_norm *)nm.p, (float *)out.p, st);
+    float *out = hc.result(2, out_b);
+    if (!out) return cuda_fail(cudaGetLastError(), "cudaMalloc");
+    rc = b200aa_chromagram(plan, hc.sig, dtype, 1, n_samples, n_samples, hc.norm, out, hc.st);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(h_out, out.p, out_b, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    return B200AA_OK;
+    if ((rc = hc.download(h_out, out, out_b))) return rc;
+    return hc.finish();
 }
 
 extern "C" int b200aa_mid_features_host(const b200aa_plan *plan, const void *h_sig, int dtype, int64_t n_samples,
                                         int ratio, int step_ratio, float *h_mid, float *h_st)
 {
     if (!plan || !h_sig || !h_mid || ratio < 1 || step_ratio < 1 || (dtype != 0 && dtype != 1)) return B200AA_ERR_INVALID;
+    if (plan->tables_status == B200AA_ERR_MEL_RANGE) return B200AA_ERR_MEL_RANGE;
     const int64_t T = b200aa_host::num_frames(n_samples, plan->window, plan->step);
     if (T == 0) return B200AA_ERR_TOO_SHORT;
+    if (plan->tables_status != B200AA_OK) return plan->tables_status;
     const int64_t M = b200aa_mid_windows(T, step_ratio);
-    const size_t in_b = size_t(n_samples) * (dtype == 0 ? 2 : 4), st_b = size_t(68) * T * 4, mid_b = size_t(136) * M * 4;
-    b200aa_plan *pl = const_cast<b200aa_plan *>(plan);
-    std::lock_guard<std::mutex> hold(pl->host_mu);
-    DevBuf sig, nm, stb, mid;
-    if (sig.alloc_from(pl, 0, in_b) || nm.alloc_from(pl, 1, sizeof(b200aa_clip_norm)) || stb.alloc_from(pl, 2, st_b) ||
-        mid.alloc_from(pl, 3, mid_b))
-        return cuda_fail(cudaGetLastError(), "cudaMalloc");
-    cudaStream_t st = nullptr;
-    CK(cudaMemcpyAsync(sig.p, h_sig, in_b, cudaMemcpyHostToDevice, st));
-    int rc = b200aa_clip_stats(sig.p, dtype, 1, n_samples, n_samples, nullptr, (b200aa_clip_norm *)nm.p, st);
+    const size_t st_b = size_t(68) * T * 4, mid_b = size_t(136) * M * 4;
+    HostCall hc(plan);
+    int rc = hc.upload(h_sig, dtype, 1, n_samples);
     if (rc) return rc;
-    rc = b200aa_st_features(plan, sig.p, dtype, 1, n_samples, n_samples, nullptr, (b200aa_clip_norm *)nm.p, 1, (float *)stb.p, T, st);
+    float *stf = hc.result(2, st_b), *mid = hc.result(3, mid_b);
+    if (!stf || !mid) return cuda_fail(cudaGetLastError(), "cudaMalloc");
+    rc = b200aa_st_features(plan, hc.sig, dtype, 1, n_samples, n_samples, nullptr, hc.norm, 1, stf, T, hc.st);
     if (rc) return rc;
-    rc = b200aa_mid_pool((const float *)stb.p, 1, 68, T, T, ratio, step_ratio, (float *)mid.p, st);
+    rc = b200aa_mid_pool(stf, 1, 68, T, T, ratio, step_ratio, mid, hc.st);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(h_mid, mid.p, mid_b, cudaMemcpyDeviceToHost, st));
-    if (h_st) CK(cudaMemcpyAsync(h_st, stb.p, st_b, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    return B200AA_OK;
+    if ((rc = hc.download(h_mid, mid, mid_b))) return rc;
+    if (h_st && (rc = hc.download(h_st, stf, st_b))) return rc;
+    return hc.finish();
 }

@@ -924,7 +924,7 @@ inline int fast_launch_t(const FastTables &ft, StParams p, int sm_count, int64_t
     unsigned int *ctr = ft.d_counters + (ft.next_counter.fetch_add(1u, std::memory_order_relaxed) % kCounterRing);
     if (cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st) != cudaSuccess) return B200AA_ERR_CUDA;
     kern<<<(unsigned)grid, NT, smem, st>>>(p, ft.d_tw, ft.d_twp, ctr);
-    return cudaGetLastError() == cudaSuccess ? B200AA_OK : B200AA_ERR_CUDA;
+    return cudaPeekAtLastError() == cudaSuccess ? B200AA_OK : B200AA_ERR_CUDA;    // the caller fetches (and clears) the text
 }
 
 // run staging needs whole 8-sample runs per frame, per entropy block (window % 80 == 0) and per hop

@@ -90,6 +90,27 @@ def test_mid_awkward_ratio(P, golden_synth):
     check_close(mid, golden_synth["mid_16000_8000"], "mid 1.0/0.5 s")
 
 
+@pytest.mark.parametrize("fs,w,s,n,exc,text", [
+    (4000, 100, 50, 50, IndexError, None),             # mel bank fails before the (empty) frame loop
+    (4000, 100, 50, 1000, IndexError, None),
+    (4000, 400, 200, 100, IndexError, None),
+    (8000, 160, 80, 100, ValueError, "need at least one array"),   # no frames: the chroma scatter is never reached
+    (8000, 160, 80, 1000, ValueError, "chroma"),
+])
+def test_error_precedence(P, fs, w, s, n, exc, text):
+    """Exception types of the unmodified reference on these inputs (tests/test_oracle_vs_reference.py checks
+    the oracle against it where the reference tree exists)."""
+    x = O.synth_clip(1, n, fs)
+    for fn in (lambda: P.ShortTermFeatures.feature_extraction(x, fs, w, s),
+               lambda: P.MidTermFeatures.mid_feature_extraction(x, fs, 4 * w, 4 * w, w, s)):
+        with pytest.raises(exc) as e:
+            fn()
+        if text:
+            assert text in str(e.value)
+        with pytest.raises(exc):
+            O.feature_extraction(x, fs, w, s)
+
+
 def test_edges(P, golden_edges):
     g = golden_edges
     S = P.ShortTermFeatures

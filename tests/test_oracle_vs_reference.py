@@ -84,3 +84,18 @@ def test_tables_match_reference(REF):
         X = rng.random(K)
         ref = S.chroma_features(X, fs, K)[1][:, 0]
         np.testing.assert_allclose(O.chroma_operator(fs, K) @ (X ** 2) / (X ** 2).sum(), ref, rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("fs,w,s,n", [(4000, 100, 50, 50), (4000, 100, 50, 1000), (8000, 160, 80, 100),
+                                      (8000, 160, 80, 1000), (4000, 400, 200, 100), (16000, 800, 400, 799)])
+def test_error_precedence(REF, fs, w, s, n):
+    """mel bank IndexError (before the loop) > no frames ValueError > chroma ValueError (frame 0)."""
+    S, M, A = REF
+    x = O.synth_clip(1, n, fs)
+    with pytest.raises((ValueError, IndexError)) as ref:
+        S.feature_extraction(x, fs, w, s)
+    with pytest.raises(ref.type) as got:
+        O.feature_extraction(x, fs, w, s)
+    assert ("need at least one array" in str(ref.value)) == ("need at least one array" in str(got.value))
+    with pytest.raises(ref.type):
+        O.feature_extraction_loop(x, fs, w, s)
