@@ -43,6 +43,17 @@ def mid_feature_extraction(signal, sampling_rate, mid_window, mid_step, short_wi
 VERBOSE = True      # the reference prints one "Analyzing file ..." line per file
 
 
+def _reference_beat_extraction():
+    """The reference's beat_extraction (host code that stays in pyAudioAnalysis; install() does not rebind it)."""
+    try:
+        import importlib
+        return importlib.import_module("pyAudioAnalysis.MidTermFeatures").beat_extraction
+    except Exception as exc:
+        raise NotImplementedError("compute_beat=True needs pyAudioAnalysis.MidTermFeatures.beat_extraction (peak picking "
+                                  "on the host, not part of the GPU path); install pyAudioAnalysis or pass "
+                                  "compute_beat=False as multiple_directory_feature_extraction does") from exc
+
+
 def _read_wav(path):
     """audioBasicIO.read_audio_file for .wav (:99) + stereo_to_mono (:156-168)."""
     from scipy.io import wavfile
@@ -60,14 +71,14 @@ def directory_feature_extraction(folder_path, mid_window, mid_step, short_window
 
     Window arguments are in seconds.  Returns (features [n_files x 136] -- a 1-D vector for a single file and an
     empty array for none, exactly like the reference's np.vstack logic --, file list, feature names).  Only .wav
-    files are decoded here (other containers need ffmpeg / pydub on the host and are skipped with a note), and the
-    beat features of ``compute_beat=True`` are outside the GPU path.
+    files are decoded here (other containers need ffmpeg / pydub on the host and are skipped with a note).
+    ``compute_beat=True`` appends the reference's own ``beat_extraction`` (MidTermFeatures.py:17-84, host-side peak
+    picking, outside the GPU path -- SURVEY 8f rank 4) applied to the GPU short-term features; it needs an importable
+    ``pyAudioAnalysis`` and raises NotImplementedError without one.
     """
     import torch
     from .batch import mid_feature_extraction_batch, long_term_mean_batch
-    if compute_beat:
-        raise NotImplementedError("compute_beat=True (beat_extraction / peakdet) is not part of the GPU path; "
-                                  "call with compute_beat=False as multiple_directory_feature_extraction does")
+    beat_extraction = _reference_beat_extraction() if compute_beat else None
     types = ('*.wav', '*.aif', '*.aiff', '*.mp3', '*.au', '*.ogg')
     files = []
     for t in types:
@@ -104,18 +115,28 @@ def directory_feature_extraction(folder_path, mid_window, mid_step, short_window
     for idx, (fs, x) in enumerate(signals):
         clip, code = _as_clip(x)
         groups.setdefault((int(fs), clip.shape[0], code), []).append((idx, clip))
+    beats = [None] * len(kept)
     for (fs, n, code), members in groups.items():
         host = np.stack([c for _, c in members])
         dev = torch.from_numpy(host).cuda()
-        mid, _ = mid_feature_extraction_batch(dev, fs, round(mid_window * fs), round(mid_step * fs),
-                                              round(fs * short_window), round(fs * short_step))
+        mid, st = mid_feature_extraction_batch(dev, fs, round(mid_window * fs), round(mid_step * fs),
+                                               round(fs * short_window), round(fs * short_step))
         lt = long_term_mean_batch(mid).cpu().numpy().astype(np.float64)
-        for (idx, _), v in zip(members, lt):
-            vectors[idx] = v
+        st_h = st.cpu().numpy().astype(np.float64) if compute_beat else None
+        for k, (idx, _) in enumerate(members):
+            vectors[idx] = lt[k]
+            if compute_beat:
+                beats[idx] = beat_extraction(st_h[k], short_step)              # reference :191
     out, out_files = np.array([]), []
-    for path, v in zip(kept, vectors):
+    appended = False
+    for path, v, beat in zip(kept, vectors, beats):
         out_files.append(path)
         if (not np.isnan(v).any()) and (not np.isinf(v).any()):      # reference :203-204
+            if compute_beat:
+                v = np.append(np.append(v, beat[0]), beat[1])        # :205-208
+                if not appended:
+                    names = names + ["bpm", "ratio"]
+                    appended = True
             out = v if len(out) == 0 else np.vstack((out, v))
     return out, out_files, names
 

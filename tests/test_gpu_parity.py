@@ -179,7 +179,7 @@ def test_batch_and_ragged(P):
         check_features(outf[i].cpu().numpy(), O.feature_extraction(clips[i], 16000, 800, 400, deltas=False)[0], 400, f"f32 clip {i}")
 
 
-def test_directory_feature_extraction(P, tmp_path):
+def test_directory_feature_extraction(P, tmp_path, monkeypatch):
     """long-term averaged mid-term vectors per file of a folder, against the reference's own output
     on its 3_class test clips (8 kHz, 1 s, 12 per class; the silence class exercises near-digital-silence audio)."""
     from scipy.io import wavfile
@@ -199,8 +199,26 @@ def test_directory_feature_extraction(P, tmp_path):
         check_close(feats, g[cls + "_feats"], f"directory_feature_extraction {cls}", rtol=2e-4, atol=2e-5)
     f3, classes, fn3 = P.MidTermFeatures.multiple_directory_feature_extraction(dirs, 1.0, 1.0, 0.05, 0.05)
     assert classes == ["music", "silence", "speech"] and len(f3) == 3 and f3[0].shape == (12, 136)
+    # compute_beat (the default) delegates to the reference's own host-side beat_extraction on the GPU short-term rows
+    import sys
+    import types
+    monkeypatch.setitem(sys.modules, "pyAudioAnalysis", None)
+    monkeypatch.setitem(sys.modules, "pyAudioAnalysis.MidTermFeatures", None)
     with pytest.raises(NotImplementedError):
-        P.MidTermFeatures.directory_feature_extraction(dirs[0], 1.0, 1.0, 0.05, 0.05)      # compute_beat defaults to True
+        P.MidTermFeatures.directory_feature_extraction(dirs[0], 1.0, 1.0, 0.05, 0.05)
+    seen = []
+    stub = types.ModuleType("pyAudioAnalysis.MidTermFeatures")
+    stub.beat_extraction = lambda st, win: (seen.append((st.shape, st.dtype, win)) or (120.0 + len(seen), 0.25))
+    pkg = types.ModuleType("pyAudioAnalysis")
+    pkg.MidTermFeatures = stub
+    monkeypatch.setitem(sys.modules, "pyAudioAnalysis", pkg)
+    monkeypatch.setitem(sys.modules, "pyAudioAnalysis.MidTermFeatures", stub)
+    fb, _, nb = P.MidTermFeatures.directory_feature_extraction(dirs[0], 1.0, 1.0, 0.05, 0.05)
+    assert fb.shape == (12, 138) and nb == list(g["names"]) + ["bpm", "ratio"]
+    assert seen[0] == ((68, 20), np.float64, 0.05) and len(seen) == 12
+    np.testing.assert_array_equal(fb[:, 136], 121.0 + np.arange(12))
+    np.testing.assert_array_equal(fb[:, 137], 0.25)
+    check_close(fb[:, :136], g["music_feats"], "directory_feature_extraction with beat", rtol=2e-4, atol=2e-5)
     one = tmp_path / "one"
     one.mkdir()
     wavfile.write(str(one / "a.wav"), int(g["fs"]), g["music_x"][0])
