@@ -8,8 +8,11 @@ Parity status: PINNED.  ``tests/test_oracle_golden.py`` checks every function
 here against golden vectors produced by the unmodified reference
 (``/root/reference`` imported through ``oracle/ref_import.py``; generator:
 ``oracle/make_golden.py``; fixtures: ``tests/golden/*.npz``).  The reference's
-own tests pin shapes only (pytests/test_feature_extraction.py:14-15,27-28);
-those shape pins are reproduced in ``tests/test_reference_pins.py``.
+own tests pin shapes only (pytests/test_feature_extraction.py:14-15,27-28;
+those shape pins are reproduced in ``tests/test_oracle_golden.py::
+test_reference_pytest_inputs``).  ``tests/test_oracle_vs_reference.py`` additionally runs the oracle against the
+imported reference on randomised configurations and error cases wherever the
+reference tree is present.
 
 Third-party arithmetic: the reference takes its DFT and DCT from SciPy
 (``scipy.fftpack.fft`` ShortTermFeatures.py:5,617 and
