@@ -295,7 +295,8 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": WORKLOAD, "clips_per_gpu": B, "frames_per_clip": T, "parallelism": "clips sharded per GPU" +
                        (", async NCCL gather of every rank's [clips,68,T] block to rank 0 per step (double-buffered: the gather of step i overlaps the kernels of step i+1; all gathers complete inside the timed region)" if world > 1 else ""),
                        "l2": "inputs larger than L2 (320 MB int16 clips + 108 MB output per step vs 126 MB L2); no explicit flush",
-                       "kernel_kind": plan.kernel_kind()},
+                       "kernel_kind": plan.kernel_kind(),
+                       **({"lib_override": os.environ["B200AA_LIB"]} if os.environ.get("B200AA_LIB") else {})},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "fused short-term feature kernel",
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,

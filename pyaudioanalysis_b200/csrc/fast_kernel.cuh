@@ -12,6 +12,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 #include "common.cuh"
 #include "dft_codelets.cuh"
@@ -24,6 +25,23 @@ namespace b200aa {
 #ifndef B200AA_FAST_MINBLOCKS
 #define B200AA_FAST_MINBLOCKS 3   // CTAs per SM the fast kernel is compiled for (register budget)
 #endif
+// Experimental "lean" build (-DB200AA_FAST_LEAN=1, see scripts/build_variants.py): the run-staged feature kernels are
+// compiled for 4 CTAs per SM (64 registers) and put on a shared-memory diet to fit 56 KB per CTA -- twiddles and the
+// mel / DCT / chroma tables are read through L1 (__ldg) instead of being copied to shared memory, one carried |X| row
+// instead of two, 16-bit sign-flip words, no unused per-lane tables.  Off by default: not yet measured on a B200.
+#ifndef B200AA_FAST_LEAN
+#define B200AA_FAST_LEAN 0
+#endif
+constexpr bool kLeanBuild = B200AA_FAST_LEAN != 0;
+__host__ __device__ constexpr bool fast_is_lean(bool runs, int mode) { return kLeanBuild && runs && mode == kModeFeatures; }
+__host__ __device__ constexpr int fast_min_blocks(bool runs, int mode) { return fast_is_lean(runs, mode) ? 4 : B200AA_FAST_MINBLOCKS; }
+// table element: shared memory (default) or global memory through the read-only L1 path (lean build)
+template <bool GL, typename T>
+__device__ __forceinline__ T tld(const T *p)
+{
+    if constexpr (GL) return __ldg(p);
+    else return *p;
+}
 
 template <int R> struct RFactors;
 template <> struct RFactors<10> { static constexpr int A = 2, B = 5; };
@@ -236,8 +254,8 @@ __device__ __forceinline__ void spectral_features_h(const float *X, const float 
 }
 
 // time-domain rows of two frames per warp (half-warp each; lanes 0..9 of a half own the ten entropy blocks)
-template <int N>
-__device__ __forceinline__ void time_features_runs_h(const float *runE, const int *runF, float *fv, int l, bool active)
+template <int N, typename RF>
+__device__ __forceinline__ void time_features_runs_h(const float *runE, const RF *runF, float *fv, int l, bool active)
 {
     constexpr int RPB = N / 80;
     float e = 0.f;
@@ -268,7 +286,7 @@ __device__ __forceinline__ void time_features_runs_h(const float *runE, const in
 // ---- mel + raw chroma on the upper half of the CTA (threads NT/2 .. NT-1) while the lower half runs the dense
 // pass: 16 threads per frame, every thread a group of <= 3 filters with balanced tap totals; then 12 threads per
 // frame for the chroma tap sums
-template <int G>
+template <int G, bool GL = false>
 __device__ __forceinline__ void upper_mel_chroma(const float *Xrows, int Kp, int ng, const SmallTables &tb, const int *grp_tab,
                                                  float *ms, float *chr, int t)
 {
@@ -278,12 +296,12 @@ __device__ __forceinline__ void upper_mel_chroma(const float *Xrows, int Kp, int
             const float *X = Xrows + size_t(f) * Kp;
 #pragma unroll
             for (int h = 0; h < 3; ++h) {
-                const int i = grp_tab[3 * sub + h];
+                const int i = tld<GL>(grp_tab + 3 * sub + h);
                 if (i >= 0) {
-                    const int s0 = tb.mel_start[i], cnt = tb.mel_count[i], off = tb.mel_off[i];
+                    const int s0 = tld<GL>(tb.mel_start + i), cnt = tld<GL>(tb.mel_count + i), off = tld<GL>(tb.mel_off + i);
                     float acc = 0.f;
 #pragma unroll 4
-                    for (int q = 0; q < cnt; ++q) acc = fmaf(X[s0 + q], tb.mel_w[off + q], acc);
+                    for (int q = 0; q < cnt; ++q) acc = fmaf(X[s0 + q], tld<GL>(tb.mel_w + off + q), acc);
                     ms[f * B200AA_N_MEL + i] = 0.30102999566398120f * flog2(acc + B200AA_EPS);   // log10
                 }
             }
@@ -293,11 +311,11 @@ __device__ __forceinline__ void upper_mel_chroma(const float *Xrows, int Kp, int
         const int f = t / 12, c = t - f * 12;
         if (f < ng) {
             const float *X = Xrows + size_t(f) * Kp;
-            const int e0 = tb.chr_off[c], e1 = tb.chr_off[c + 1];
+            const int e0 = tld<GL>(tb.chr_off + c), e1 = tld<GL>(tb.chr_off + c + 1);
             float acc = 0.f;
             for (int e = e0; e < e1; ++e) {
-                const float v = X[tb.chr_bin[e]];
-                acc = fmaf(v * v, tb.chr_w[e], acc);
+                const float v = X[tld<GL>(tb.chr_bin + e)];
+                acc = fmaf(v * v, tld<GL>(tb.chr_w + e), acc);
             }
             chr[f * 12 + c] = acc;
         }
@@ -322,7 +340,7 @@ __device__ __forceinline__ void chroma_finalize_h(const float *chroma_raw, float
 //   y_c = sum_{n<20} D[c][n] * ((m_n - k) + (-1)^c (m_{39-n} - k)),  k = m_0 (any constant works for
 //   c >= 1 because those rows are orthogonal to constants; row 0 adds it back): keeps the float32 sum
 //   free of the large common offset of the log-mel values.
-template <int G>
+template <int G, bool GL = false>
 __device__ __forceinline__ void flat_dct(const float *ms, int ng, const SmallTables &tb, float *fvrows, int fbase, int tid)
 {
     const int f = tid / 26, r = tid - f * 26;
@@ -338,7 +356,7 @@ __device__ __forceinline__ void flat_dct(const float *ms, int ng, const SmallTab
         for (int j = 0; j < 10; ++j) {
             const int n = 10 * h + j;
             const float a = m[n] - kap, b = m[39 - n] - kap;
-            acc = fmaf(row[n], fmaf(sgn, b, a), acc);
+            acc = fmaf(tld<GL>(row + n), fmaf(sgn, b, a), acc);
         }
     }
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
@@ -359,8 +377,9 @@ __device__ __forceinline__ void flat_dct(const float *ms, int ng, const SmallTab
 // a frame are sums over its 100 runs and the 50 % overlap is computed once.
 // ----------------------------------------------------------------------------------------------
 
+template <typename RF>
 __device__ __forceinline__ void stage_run(const void *clip, int dtype, bool vec_ok, int64_t n0, const b200aa_clip_norm &nm,
-                                          float *dst, float *runE, int *runF)
+                                          float *dst, float *runE, RF *runF)
 {
     float d[8];
     if (dtype == B200AA_DTYPE_I16) {
@@ -407,7 +426,7 @@ __device__ __forceinline__ void stage_run(const void *clip, int dtype, bool vec_
     *reinterpret_cast<float4 *>(dst) = make_float4(d[0], d[1], d[2], d[3]);
     *reinterpret_cast<float4 *>(dst + 4) = make_float4(d[4], d[5], d[6], d[7]);
     *runE = e;
-    *runF = fli | (link << 8);
+    *runF = RF(fli | (link << 8));
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -441,8 +460,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 }
 
 // stage_run() with the 8 int16 samples (and their predecessor) already in shared memory
+template <typename RF>
 __device__ __forceinline__ void stage_run_smem(const short *raw8, bool has_pred, const b200aa_clip_norm &nm, float *dst, float *runE,
-                                               int *runF)
+                                               RF *runF)
 {
     const int4 q = *reinterpret_cast<const int4 *>(raw8);
     const int w4[4] = {q.x, q.y, q.z, q.w};
@@ -465,7 +485,7 @@ __device__ __forceinline__ void stage_run_smem(const short *raw8, bool has_pred,
     *reinterpret_cast<float4 *>(dst) = make_float4(d[0], d[1], d[2], d[3]);
     *reinterpret_cast<float4 *>(dst + 4) = make_float4(d[4], d[5], d[6], d[7]);
     *runE = e;
-    *runF = int(fl) | (int(linkf) << 8);
+    *runF = RF(int(fl) | (int(linkf) << 8));
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -503,20 +523,20 @@ struct FastShape {
     static constexpr int NT = 32 * G;            // threads per CTA
 };
 
-// fixed-size part of the CTA's shared memory (compile-time offsets)
-template <int R1, int R2, int G>
+// fixed-size part of the CTA's shared memory (compile-time offsets); LEAN = the 4-CTAs-per-SM layout of the lean build
+template <int R1, int R2, int G, bool LEAN = false>
 struct alignas(16) FastFixed {
     using S = FastShape<R1, R2, G>;
     float2 E[G * R1 * S::ES];              // transpose buffer [G][R][ES]; the |X| rows alias it
-    float2 tw[R1 * R2];                   // W_Nc^(k1 n2)  [k1][n2]
-    float2 twp[(S::Nc / 2 + 2) & ~1];     // W_N^k
-    alignas(16) float Xprev[2 * S::Kp];   // |X| of the previous step's last frame (double-buffered)
+    float2 tw[LEAN ? 2 : R1 * R2];        // W_Nc^(k1 n2)  [k1][n2]   (lean: read from global memory)
+    float2 twp[LEAN ? 2 : ((S::Nc / 2 + 2) & ~1)];     // W_N^k
+    alignas(16) float Xprev[(LEAN ? 1 : 2) * S::Kp];   // |X| of the previous step's last frame (double-buffered; lean: one row, copied in the store phase)
     float fvrows[(G + 1) * kFvStride];    // ring of feature rows: 34 features + the row's sum(X) in slot 34
     float mscr[G * B200AA_N_MEL];         // log-mel energies
     float chr[G * 12];                    // raw chroma sums
-    float parts[G * 64];                  // entropy parts per warp
-    alignas(16) int dlane[32 * 4];        // per-lane constants of the dense pass
-    alignas(16) int4 tlane[32];           // per-lane constants of the chunked time-domain pass (non-run kernels)
+    float parts[LEAN ? G * 32 : G * 64];  // entropy parts per (dense) half-warp; the chunked time-domain pass needs 64 per warp
+    alignas(16) int dlane[(LEAN ? 16 : 32) * 4];        // per-lane constants of the dense pass
+    alignas(16) int4 tlane[LEAN ? 1 : 32];              // per-lane constants of the chunked time-domain pass (non-run kernels)
     unsigned int next_item;
     alignas(8) unsigned long long mbar;   // completion barrier of the TMA prefetch
 };
@@ -524,39 +544,50 @@ struct alignas(16) FastFixed {
 template <int R1, int R2, int G>
 inline size_t fast_fixed_bytes() { return sizeof(FastFixed<R1, R2, G>); }
 template <int R1, int R2, int G>
-inline size_t fast_smem_bytes(int step, int blob_words, bool runs)
+inline size_t fast_smem_bytes(int step, int blob_words, bool runs, bool lean = false)
 {
     using S = FastShape<R1, R2, G>;
     const size_t span_max = size_t(G - 1) * step + S::N;
-    const size_t nrun = (span_max / 8 + 4) & ~size_t(3);
     // see the kernel: with run staging the carried tail must survive, otherwise the whole span is dead after pass 1
     const bool zs_alias = runs ? size_t(G) * step >= 2 * size_t(G) * S::ZS : span_max >= 2 * size_t(G) * S::ZS;
+    if (lean) {     // no table blob, 16-bit flip words (run count padded to 8 so the sample span stays 16-byte aligned)
+        const size_t nrun8 = (span_max / 8 + 8) & ~size_t(7);
+        return sizeof(FastFixed<R1, R2, G, true>) + (sizeof(float) + sizeof(unsigned short)) * nrun8 +
+               sizeof(float) * (span_max + 8) + (zs_alias ? 0 : sizeof(float2) * G * S::ZS) +
+               sizeof(short) * (size_t(G) * step + 16);
+    }
+    const size_t nrun = (span_max / 8 + 4) & ~size_t(3);
     return fast_fixed_bytes<R1, R2, G>() + sizeof(int) * ((blob_words + 3) & ~3) + 2 * sizeof(float) * nrun +
            sizeof(float) * (span_max + 8) + (zs_alias ? 0 : sizeof(float2) * G * S::ZS) +
            (runs ? sizeof(short) * (size_t(G) * step + 16) : 0);
 }
 
 template <int R1, int R2, int G, bool STEP_EVEN, bool RUNS, int MODE>
-__global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(const StParams p, const float2 *__restrict__ g_tw,
+__global__ void __launch_bounds__(32 * G, fast_min_blocks(RUNS, MODE)) st_fast_kernel(const StParams p, const float2 *__restrict__ g_tw,
                                                                 const float2 *__restrict__ g_twp, unsigned int *work_counter)
 {
     using S = FastShape<R1, R2, G>;
     constexpr int Nc = S::Nc, N = S::N, K = S::K, Kp = S::Kp, ES = S::ES, H = S::H, ZS = S::ZS, NT = S::NT, TPF = S::TPF;
+    constexpr bool LEAN = fast_is_lean(RUNS, MODE);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int step = p.step;
     // shared-memory layout: all fixed-size arrays sit at compile-time offsets (no address arithmetic to keep
     // live in registers); the three arrays whose size depends on the hop come last
-    using Fixed = FastFixed<R1, R2, G>;
+    using Fixed = FastFixed<R1, R2, G, LEAN>;
     Fixed &sm = *reinterpret_cast<Fixed *>(smem_raw);
     float2 *const E = sm.E, *const s_tw = sm.tw, *const s_twp = sm.twp;
     float *const Xprev = sm.Xprev, *const fvrows = sm.fvrows, *const mscr = sm.mscr, *const chr = sm.chr;
     float *const parts = sm.parts;
     int *const blob_s = reinterpret_cast<int *>(smem_raw + sizeof(Fixed));
-    const int blob_pad = (p.bl.words + 3) & ~3;
-    const int nrun = ((G - 1) * step + N) / 8 + 4 & ~3;
+    const int blob_pad = LEAN ? 0 : (p.bl.words + 3) & ~3;
+    const int nrun = LEAN ? (((G - 1) * step + N) / 8 + 8 & ~7) : (((G - 1) * step + N) / 8 + 4 & ~3);
+    using runf_t = std::conditional_t<LEAN, unsigned short, int>;                     // sign-flip word of a run
     float *const runE = reinterpret_cast<float *>(blob_s + blob_pad);                 // run partials (RUNS only)
-    int *const runF = reinterpret_cast<int *>(runE + nrun);
+    runf_t *const runF = reinterpret_cast<runf_t *>(runE + nrun);
     float *const sS = reinterpret_cast<float *>(runF + nrun);                         // sample span
+    // twiddles: shared memory, or (lean) global memory through L1
+    auto TW = [&](int i) -> float2 { if constexpr (LEAN) return __ldg(g_tw + i); else return s_tw[i]; };
+    auto TWP = [&](int i) -> float2 { if constexpr (LEAN) return __ldg(g_twp + i); else return s_twp[i]; };
     // published second-pass outputs [G][ZS]: the float samples of the G frames are dead once pass 1 has read them
     // (with run staging only the tail that the next step reuses must survive; without it the time-domain rows are
     // produced right after staging), so Zs lives on top of them
@@ -570,17 +601,22 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
     static_assert((G & (G - 1)) == 0 && G * 26 <= NT, "tile mapping");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < p.bl.words; i += NT) blob_s[i] = p.blob[i];
-    for (int i = tid; i < R1 * R2; i += NT) s_tw[i] = g_tw[i];
-    for (int i = tid; i < Nc / 2 + 1; i += NT) s_twp[i] = g_twp[i];
-    __syncthreads();
-    const SmallTables tb = bind_tables(blob_s, p.bl);
-    if (tid < 32) sm.tlane[tid] = time_lane_init(N, tid);
+    if constexpr (!LEAN) {
+        for (int i = tid; i < p.bl.words; i += NT) blob_s[i] = p.blob[i];
+        for (int i = tid; i < R1 * R2; i += NT) s_tw[i] = g_tw[i];
+        for (int i = tid; i < Nc / 2 + 1; i += NT) s_twp[i] = g_twp[i];
+        __syncthreads();
+    }
+    const int *const blob_t = LEAN ? p.blob : blob_s;       // where the small tables are read from
+    const SmallTables tb = bind_tables(blob_t, p.bl);
+    if constexpr (!LEAN) {
+        if (tid < 32) sm.tlane[tid] = time_lane_init(N, tid);
+    }
     if (tid < 16) {
         const DenseLane d0_ = dense_lane_init_h<K>(tid);
         sm.dlane[tid * 4 + 0] = d0_.split; sm.dlane[tid * 4 + 1] = d0_.ps; sm.dlane[tid * 4 + 2] = d0_.pe;
     }
-    for (int i = tid; i < 2 * Kp; i += NT) Xprev[i] = 0.f;
+    for (int i = tid; i < (LEAN ? 1 : 2) * Kp; i += NT) Xprev[i] = 0.f;
     if (RUNS && tid == 0) mbar_init(&sm.mbar, 1);
     unsigned tma_phase = 0;       // parity of the next completion to wait for
     __syncthreads();
@@ -635,7 +671,7 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
                     keep = N - step;                       // previous step was a full one (G frames)
                     // up to 2 float4 + 1 run partial per thread (keep <= N - 8 samples)
                     float4 cv[2];
-                    float ce[1]; int cf[1];
+                    float ce[1]; runf_t cf[1];
                     const int src = G * step;
                     static_assert((2 * Nc) / 4 <= 2 * NT && (2 * Nc) / 8 <= NT, "carry copy mapping");
 #pragma unroll
@@ -700,7 +736,7 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
                 float2 *Ef = E + size_t(ff) * R1 * ES;
 #pragma unroll
                 for (int k1 = 0; k1 < R1; ++k1) {
-                    const float2 w = k1 == 0 ? make_float2(1.f, 0.f) : s_tw[k1 * R2 + fj];
+                    const float2 w = k1 == 0 ? make_float2(1.f, 0.f) : TW(k1 * R2 + fj);
                     Ef[k1 * ES + fj] = k1 == 0 ? v1[0] : cmul(v1[k1], w);
                 }
             }
@@ -726,7 +762,7 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
                     const float2 zp = Zf[(Nc - k) - R1 * H];
                     const float2 ev = make_float2(zk.x + zp.x, zk.y - zp.y);
                     const float2 od = make_float2(zk.y + zp.y, zp.x - zk.x);
-                    const float2 t = cmul(od, s_twp[k]);
+                    const float2 t = cmul(od, TWP(k));
                     const float ar = ev.x + t.x, ai = ev.y + t.y;
                     const float br = ev.x - t.x, bi = ev.y - t.y;
                     Xf[k] = fsqrt_pos(fmaf(ar, ar, ai * ai)) * sc;
@@ -789,7 +825,7 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
             if (rr > G) rr -= G + 1;
             float *fv = fvrows + rr * kFvStride;
             if (warp >= G / 2) {
-                upper_mel_chroma<G>(Xrows, Kp, ng, tb, blob_s + p.bl.mel_grp, mscr, chr, tid - NT / 2);
+                upper_mel_chroma<G, LEAN>(Xrows, Kp, ng, tb, blob_t + p.bl.mel_grp, mscr, chr, tid - NT / 2);
             } else {
                 const fidx_t fr = g0 + f;
                 const float *X = Xrows + size_t(f) * Kp;
@@ -799,17 +835,26 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
                 const float rs = row_sum_h<K>(Xp, l16);
                 const float sxp = (has_prev && f == 0) ? fvrows[fbase * kFvStride + 34] : rs;
                 spectral_features_h<K>(X, Xp, sxp, sm.dlane + l16 * 4, parts + (warp * 2 + half) * 32, fv, l16, act,
-                                       (act && f == ng - 1) ? Xprev + (xsel ^ 1) * Kp : nullptr);
+                                       (!LEAN && act && f == ng - 1) ? Xprev + (xsel ^ 1) * Kp : nullptr);
             }
             __syncthreads();
             // ---- phase B: DCT rows (all threads), then chroma normalisation (lower half) / time-domain rows (upper half)
-            flat_dct<G>(mscr, ng, tb, fvrows, fbase, tid);
+            flat_dct<G, LEAN>(mscr, ng, tb, fvrows, fbase, tid);
             if (warp >= G / 2) {
                 if (RUNS) time_features_runs_h<N>(runE + (f * step) / 8, runF + (f * step) / 8, fv, l16, act);
             } else {
                 chroma_finalize_h(chr + f * 12, fv, l16, act);
             }
             __syncthreads();
+            if constexpr (LEAN) {
+                // single carried |X| row: its readers (this step's dense pass) are behind the barriers above, the next
+                // ones run after the next step's transform; the rows themselves stay intact until that step's pass 1
+                static_assert(Kp % 4 == 0 && Kp / 4 <= NT, "carry-row copy mapping");
+                if (tid >= NT - Kp / 4) {
+                    const int i = tid - (NT - Kp / 4);
+                    reinterpret_cast<float4 *>(Xprev)[i] = reinterpret_cast<const float4 *>(Xrows + size_t(ng - 1) * Kp)[i];
+                }
+            }
             // ---- store the [n_out x 8] tile: 8 consecutive threads -> 8 consecutive frames of one feature row
             float *const out_b = p.out + size_t(b) * p.n_out * p.t_stride + g0;
             for (int e = tid; e < p.n_out * G; e += NT) {
@@ -832,7 +877,7 @@ __global__ void __launch_bounds__(32 * G, B200AA_FAST_MINBLOCKS) st_fast_kernel(
             // (no copies, no barrier: the next step's writers of these arrays run several barriers later)
             fbase += ng;
             if (fbase > G) fbase -= G + 1;
-            xsel ^= 1;
+            if constexpr (!LEAN) xsel ^= 1;
         }
         } while (0);
         __syncthreads();
@@ -892,7 +937,7 @@ template <int R1, int R2, int G, bool EVEN, bool RUNS, int MODE>
 inline int fast_launch_t(const FastTables &ft, StParams p, int sm_count, int64_t T, cudaStream_t st)
 {
     constexpr int NT = 32 * G;
-    const size_t smem = fast_smem_bytes<R1, R2, G>(p.step, p.bl.words, RUNS);
+    const size_t smem = fast_smem_bytes<R1, R2, G>(p.step, p.bl.words, RUNS, fast_is_lean(RUNS, MODE));
     if (smem > 110u * 1024u) return B200AA_ERR_UNSUPPORTED;      // very large hop: leave it to the generic kernel
     auto kern = st_fast_kernel<R1, R2, G, EVEN, RUNS, MODE>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200AA_ERR_CUDA;

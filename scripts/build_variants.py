@@ -1,0 +1,57 @@
+"""Build experimental variants of libb200aa.so next to the default one (A/B runs on the GPU box).
+
+    python scripts/build_variants.py            # all variants
+    python scripts/build_variants.py lean       # one
+
+Variants land in pyaudioanalysis_b200/variants/libb200aa_<name>.so (git-ignored like every .so, shipped to the
+GPU box by gpurun) and are selected per process with the B200AA_LIB environment variable, e.g. in ONE gpurun call:
+
+    for v in "" lean; do
+      lib=${v:+$PWD/pyaudioanalysis_b200/variants/libb200aa_$v.so}
+      echo "== ${v:-default}"
+      B200AA_LIB=$lib timeout 150 python -m pytest tests -m gpu -x -q 2>&1 | tail -1
+      B200AA_LIB=$lib timeout 100 python bench.py --no-cpu --no-e2e | python -c \
+        "import json,sys; j=json.loads(sys.stdin.readlines()[-1]); print(j['roofline']['kernel_ms'], j['value'])"
+    done
+
+The default build is never affected: every variant is a compile-time switch that is off by default (the SASS of
+the default library was compared before / after the switches were added).
+"""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from pyaudioanalysis_b200 import build as B   # noqa: E402
+
+VARIANTS = {
+    # 4 CTAs / SM for the run-staged feature kernels: 64 registers, 56 KB shared memory (tables through L1,
+    # one carried |X| row, 16-bit flip words); see B200AA_FAST_LEAN in csrc/fast_kernel.cuh
+    "lean": ["-DB200AA_FAST_LEAN=1"],
+    # reference points for bisecting: scalar butterflies / IEEE MUFU wrappers
+    "nof32x2": ["-DB200AA_NO_F32X2"],
+    "noftz": ["-DB200AA_NO_FTZ_MUFU"],
+}
+
+
+def build(name, verbose=False):
+    out_dir = os.path.join(B.HERE, "variants")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, "libb200aa_%s.so" % name)
+    flags = [f for f in B.NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    cmd = [B._nvcc()] + flags + VARIANTS[name] + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", out] + [os.path.join(B.CSRC, s) for s in B.SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed building variant " + name)
+    if verbose:
+        sys.stderr.write(res.stderr)
+    return out
+
+
+if __name__ == "__main__":
+    names = [a for a in sys.argv[1:] if not a.startswith("-")] or list(VARIANTS)
+    for n in names:
+        print(build(n, verbose="-v" in sys.argv))
