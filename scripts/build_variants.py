@@ -29,6 +29,9 @@ VARIANTS = {
     # 4 CTAs / SM for the run-staged feature kernels: 64 registers, 56 KB shared memory (tables through L1,
     # one carried |X| row, 16-bit flip words); see B200AA_FAST_LEAN in csrc/fast_kernel.cuh
     "lean": ["-DB200AA_FAST_LEAN=1"],
+    # 64 registers / 4 CTAs per SM without the diet: only the small-window shapes (<= 45 KB: 320 / 400 / 480-sample
+    # windows) actually reach 4 CTAs per SM with it
+    "mb4": ["-DB200AA_FAST_MINBLOCKS=4"],
     # reference points for bisecting: scalar butterflies / IEEE MUFU wrappers
     "nof32x2": ["-DB200AA_NO_F32X2"],
     "noftz": ["-DB200AA_NO_FTZ_MUFU"],
