@@ -272,7 +272,7 @@ def run_ours(args, rank, world, local_rank):
         e2e = {"value": frames_per_step / dt, "unit": "frames/s", "h2d_bytes_per_step": int(host_in.numel() * 2),
                "d2h_bytes_per_step": int(host_out.numel() * 4), "ms_per_step": 1e3 * dt,
                "api": "pyaudioanalysis_b200.hostpipe.HostPipeline.run (pinned host int16 in, pinned host float32 out, chunked "
-                      "H2D / kernels / D2H on two streams)"}
+                      "H2D / b200aa_clip_stats + b200aa_st_features / D2H round-robin on three streams)"}
         # parity spot check of the e2e result against the device-resident result
         assert torch.equal(host_out[:4], out[:4].cpu()), "host pipeline and device path disagree"
 
