@@ -59,18 +59,20 @@ __host__ __device__ constexpr int cx_modinv(int a, int m)
 // small forward DFTs on register arrays
 // ----------------------------------------------------------------------------------------------
 // Blackwell packed FP32: one FADD2 / FFMA2 instruction handles the (re, im) pair (sm_100 FP32x2 datapath)
-#ifndef B200AA_NO_F32X2
+// (the codelets are __host__ __device__ so that tests/test_codelets_cpu.py can run them on the CPU; host code and
+// -DB200AA_NO_F32X2 builds use the scalar forms)
+#if !defined(B200AA_NO_F32X2) && defined(__CUDA_ARCH__)
 __device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
 __device__ __forceinline__ float2 f2fma(float c, float2 a, float2 acc) { return __ffma2_rn(make_float2(c, c), a, acc); }
 #else
-__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 f2fma(float c, float2 a, float2 acc) { return make_float2(fmaf(c, a.x, acc.x), fmaf(c, a.y, acc.y)); }
+__host__ __device__ __forceinline__ float2 f2add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ float2 f2fma(float c, float2 a, float2 acc) { return make_float2(fmaf(c, a.x, acc.x), fmaf(c, a.y, acc.y)); }
 #endif
 
 template <int P>
-__device__ __forceinline__ void dft_small(float2 (&x)[P])
+__host__ __device__ __forceinline__ void dft_small(float2 (&x)[P])
 {
     if constexpr (P == 2) {
         const float2 a = x[0], b = x[1];
@@ -114,7 +116,7 @@ __device__ __forceinline__ void dft_small(float2 (&x)[P])
 
 // prime-factor FFT of length RA*RB (coprime), natural order in, natural order out
 template <int RA, int RB>
-__device__ __forceinline__ void fft_pfa(float2 (&v)[RA * RB])
+__host__ __device__ __forceinline__ void fft_pfa(float2 (&v)[RA * RB])
 {
     constexpr int N = RA * RB;
     float2 U[N];
@@ -143,7 +145,7 @@ __device__ __forceinline__ void fft_pfa(float2 (&v)[RA * RB])
 // Cooley-Tukey FFT of length RA*RB with compile-time twiddles (needed when the factors are not coprime:
 // 16 = 4 x 4).  n = RB*a + b, k = ka + RA*kb.
 template <int RA, int RB>
-__device__ __forceinline__ void fft_ct(float2 (&v)[RA * RB])
+__host__ __device__ __forceinline__ void fft_ct(float2 (&v)[RA * RB])
 {
     constexpr int N = RA * RB;
     constexpr Trig<N> T = make_trig<N>();
@@ -179,6 +181,22 @@ __device__ __forceinline__ void fft_ct(float2 (&v)[RA * RB])
 #pragma unroll
         for (int kb = 0; kb < RB; ++kb) v[ka + RA * kb] = t[kb];
     }
+}
+
+// the R-point transforms of the register-tiled kernel (fast_kernel.cuh) and their factorisations
+template <int R> struct RFactors;
+template <> struct RFactors<10> { static constexpr int A = 2, B = 5; };
+template <> struct RFactors<12> { static constexpr int A = 4, B = 3; };
+template <> struct RFactors<15> { static constexpr int A = 3, B = 5; };
+template <> struct RFactors<20> { static constexpr int A = 4, B = 5; };
+template <> struct RFactors<21> { static constexpr int A = 3, B = 7; };
+template <> struct RFactors<16> { static constexpr int A = 4, B = 4; };   // not coprime: Cooley-Tukey
+
+template <int R>
+__host__ __device__ __forceinline__ void fft_r(float2 (&v)[R])
+{
+    if constexpr (R == 16) fft_ct<4, 4>(v);                                   // factors not coprime: Cooley-Tukey
+    else fft_pfa<RFactors<R>::A, RFactors<R>::B>(v);                          // prime-factor (twiddle-free)
 }
 
 }  // namespace b200aa

@@ -43,21 +43,6 @@ __device__ __forceinline__ T tld(const T *p)
     else return *p;
 }
 
-template <int R> struct RFactors;
-template <> struct RFactors<10> { static constexpr int A = 2, B = 5; };
-template <> struct RFactors<12> { static constexpr int A = 4, B = 3; };
-template <> struct RFactors<15> { static constexpr int A = 3, B = 5; };
-template <> struct RFactors<20> { static constexpr int A = 4, B = 5; };
-template <> struct RFactors<21> { static constexpr int A = 3, B = 7; };
-template <> struct RFactors<16> { static constexpr int A = 4, B = 4; };   // not coprime: Cooley-Tukey
-
-template <int R>
-__device__ __forceinline__ void fft_r(float2 (&v)[R])
-{
-    if constexpr (R == 16) fft_ct<4, 4>(v);                                   // factors not coprime: Cooley-Tukey
-    else fft_pfa<RFactors<R>::A, RFactors<R>::B>(v);                          // prime-factor (twiddle-free)
-}
-
 // ---- cheap math: MUFU-based reciprocal / rsqrt / log2 (2 ulp); the parity tolerance is 1e-4
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
 // rsqrtf() is the MUFU.RSQ approximation; __frsqrt_rn() is the correctly rounded (slow) one -- measured 12 % slower
