@@ -918,6 +918,7 @@ inline int fast_plan_init(int fs, int window, int step, const std::vector<int> &
     return B200AA_OK;
 }
 
+#ifndef B200AA_LAYOUT_ONLY     // tests/smem_budget_host.cu includes this header for the layout arithmetic only
 template <int R1, int R2, int G, bool EVEN, bool RUNS, int MODE>
 inline int fast_launch_t(const FastTables &ft, StParams p, int sm_count, int64_t T, cudaStream_t st)
 {
@@ -997,5 +998,6 @@ inline int fast_launch_rows(int kind, int mode, const FastTables &ft, const StPa
     if (mode == kModeSpectrogram) return fast_launch_mode<kModeSpectrogram>(kind, ft, p, sm_count, p.rows_launch, st);
     return fast_launch_mode<kModeChromagram>(kind, ft, p, sm_count, p.rows_launch, st);
 }
+#endif  // B200AA_LAYOUT_ONLY
 
 }  // namespace b200aa

@@ -4,15 +4,13 @@
     python scripts/build_variants.py lean       # one
 
 Variants land in pyaudioanalysis_b200/variants/libb200aa_<name>.so (git-ignored like every .so, shipped to the
-GPU box by gpurun) and are selected per process with the B200AA_LIB environment variable, e.g. in ONE gpurun call:
+GPU box by gpurun) and are selected per process with the B200AA_LIB environment variable.  One gpurun call A/Bs
+them (quick parity against the oracle + kernel timing per build):
 
-    for v in "" lean; do
-      lib=${v:+$PWD/pyaudioanalysis_b200/variants/libb200aa_$v.so}
-      echo "== ${v:-default}"
-      B200AA_LIB=$lib timeout 150 python -m pytest tests -m gpu -x -q 2>&1 | tail -1
-      B200AA_LIB=$lib timeout 100 python bench.py --no-cpu --no-e2e | python -c \
-        "import json,sys; j=json.loads(sys.stdin.readlines()[-1]); print(j['roofline']['kernel_ms'], j['value'])"
-    done
+    gpurun --timeout 300 -- 'python scripts/ab_run.py default lean mb4 | tee gpurun_out/ab.jsonl'
+
+and the full suite runs on a variant with `B200AA_LIB=$PWD/pyaudioanalysis_b200/variants/libb200aa_lean.so python -m
+pytest tests -m gpu -q`.
 
 The default build is never affected: every variant is a compile-time switch that is off by default (the SASS of
 the default library was compared before / after the switches were added).

@@ -1,0 +1,45 @@
+"""CPU: shared-memory budget of the fused kernel (csrc/fast_kernel.cuh) for the shapes the library instantiates.
+
+sm_100: 233 472 B of shared memory per SM, 1 024 B reserved per resident CTA, so n CTAs per SM need
+n * (bytes + 1024) <= 233 472.  The default layout is sized for 3 CTAs per SM on the headline shape, the lean
+layout (-DB200AA_FAST_LEAN=1, scripts/build_variants.py) for 4."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SM_BYTES, CTA_RESERVED = 233472, 1024
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if cand and os.path.exists(cand):
+            return cand
+    return None
+
+
+def ctas_per_sm(nbytes):
+    return SM_BYTES // (nbytes + CTA_RESERVED)
+
+
+@pytest.mark.skipif(_nvcc() is None, reason="nvcc not available")
+def test_shared_memory_budget(tmp_path):
+    exe = str(tmp_path / "smem_budget")
+    res = subprocess.run([_nvcc(), "-std=c++17", "-arch=sm_100a", "-o", exe, os.path.join(ROOT, "tests", "smem_budget_host.cu")],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    rows = [tuple(int(v) for v in ln.split()) for ln in subprocess.run([exe], capture_output=True, text=True).stdout.splitlines()]
+    table = {(n, s): (runs, d, lean) for n, s, runs, d, lean in rows}
+    assert len(table) == 15
+    # headline shape (50 / 25 ms @ 16 kHz): 3 CTAs per SM by default, 4 with the lean layout
+    runs, d, lean = table[(800, 400)]
+    assert runs == 1 and ctas_per_sm(d) == 3 and ctas_per_sm(lean) >= 4
+    # every instantiated shape keeps at least 2 CTAs per SM at hop = window / 2 and fits the launcher's 110 KB cap
+    for (n, s), (runs, d, lean) in table.items():
+        assert d <= 110 * 1024, (n, s, d)
+        if 2 * s <= n:
+            assert ctas_per_sm(d) >= 2, (n, s, d)
+        if runs:
+            assert lean < d
