@@ -28,13 +28,17 @@ namespace b200aa {
 // Experimental "lean" build (-DB200AA_FAST_LEAN=1, see scripts/build_variants.py): the run-staged feature kernels are
 // compiled for 4 CTAs per SM (64 registers) and put on a shared-memory diet to fit 56 KB per CTA -- twiddles and the
 // mel / DCT / chroma tables are read through L1 (__ldg) instead of being copied to shared memory, one carried |X| row
-// instead of two, 16-bit sign-flip words, no unused per-lane tables.  Off by default: not yet measured on a B200.
+// instead of two, 16-bit sign-flip words, no unused per-lane tables.  -DB200AA_FAST_LEAN=2 additionally shrinks those
+// CTAs to six warps (five transform warps + one spare; dense pass on four warps, mel / chroma on two): 4 CTAs per SM at
+// 80 registers.  Off by default: not yet measured on a B200.
 #ifndef B200AA_FAST_LEAN
 #define B200AA_FAST_LEAN 0
 #endif
 constexpr bool kLeanBuild = B200AA_FAST_LEAN != 0;
 __host__ __device__ constexpr bool fast_is_lean(bool runs, int mode) { return kLeanBuild && runs && mode == kModeFeatures; }
 __host__ __device__ constexpr int fast_min_blocks(bool runs, int mode) { return fast_is_lean(runs, mode) ? 4 : B200AA_FAST_MINBLOCKS; }
+// threads per CTA: one warp per frame slot, except the six-warp lean kernels
+__host__ __device__ constexpr int fast_threads(bool runs, int mode, int g) { return (B200AA_FAST_LEAN == 2 && fast_is_lean(runs, mode)) ? 192 : 32 * g; }
 // table element: shared memory (default) or global memory through the read-only L1 path (lean build)
 template <bool GL, typename T>
 __device__ __forceinline__ T tld(const T *p)
@@ -271,11 +275,15 @@ __device__ __forceinline__ void time_features_runs_h(const float *runE, const RF
 // ---- mel + raw chroma on the upper half of the CTA (threads NT/2 .. NT-1) while the lower half runs the dense
 // pass: 16 threads per frame, every thread a group of <= 3 filters with balanced tap totals; then 12 threads per
 // frame for the chroma tap sums
-template <int G, bool GL = false>
+template <int G, bool GL = false, int UT = 16 * G>
 __device__ __forceinline__ void upper_mel_chroma(const float *Xrows, int Kp, int ng, const SmallTables &tb, const int *grp_tab,
-                                                 float *ms, float *chr, int t)
+                                                 float *ms, float *chr, int t0)
 {
-    {
+    // UT threads (t0 < UT) share the G * 16 (frame, filter group) slots and the G * 12 (frame, pitch class) slots
+    static_assert((16 * G) % UT == 0, "whole rounds over the filter-group slots");
+#pragma unroll
+    for (int rd = 0; rd < (16 * G) / UT; ++rd) {
+        const int t = t0 + rd * UT;
         const int f = t >> 4, sub = t & 15;
         if (f < ng) {
             const float *X = Xrows + size_t(f) * Kp;
@@ -292,7 +300,10 @@ __device__ __forceinline__ void upper_mel_chroma(const float *Xrows, int Kp, int
             }
         }
     }
-    if (t < G * 12) {
+#pragma unroll
+    for (int rd = 0; rd < (G * 12 + UT - 1) / UT; ++rd) {
+        const int t = t0 + rd * UT;
+        if (t >= G * 12) continue;
         const int f = t / 12, c = t - f * 12;
         if (f < ng) {
             const float *X = Xrows + size_t(f) * Kp;
@@ -325,9 +336,13 @@ __device__ __forceinline__ void chroma_finalize_h(const float *chroma_raw, float
 //   y_c = sum_{n<20} D[c][n] * ((m_n - k) + (-1)^c (m_{39-n} - k)),  k = m_0 (any constant works for
 //   c >= 1 because those rows are orthogonal to constants; row 0 adds it back): keeps the float32 sum
 //   free of the large common offset of the log-mel values.
-template <int G, bool GL = false>
-__device__ __forceinline__ void flat_dct(const float *ms, int ng, const SmallTables &tb, float *fvrows, int fbase, int tid)
+template <int G, bool GL = false, int NT = 32 * G>
+__device__ __forceinline__ void flat_dct(const float *ms, int ng, const SmallTables &tb, float *fvrows, int fbase, int tid0)
 {
+    static_assert(NT % 2 == 0, "the two halves of a row sit in neighbouring lanes");
+#pragma unroll
+    for (int base = 0; base < G * 26; base += NT) {       // every thread runs every round (the shuffle needs whole warps)
+    const int tid = base + tid0;
     const int f = tid / 26, r = tid - f * 26;
     const int c = r >> 1, h = r & 1;
     float acc = 0.f;
@@ -350,6 +365,7 @@ __device__ __forceinline__ void flat_dct(const float *ms, int ng, const SmallTab
         int r = fbase + 1 + f;
         if (r > G) r -= G + 1;
         fvrows[r * kFvStride + 8 + c] = acc;
+    }
     }
 }
 
@@ -548,12 +564,15 @@ inline size_t fast_smem_bytes(int step, int blob_words, bool runs, bool lean = f
 }
 
 template <int R1, int R2, int G, bool STEP_EVEN, bool RUNS, int MODE>
-__global__ void __launch_bounds__(32 * G, fast_min_blocks(RUNS, MODE)) st_fast_kernel(const StParams p, const float2 *__restrict__ g_tw,
+__global__ void __launch_bounds__(fast_threads(RUNS, MODE, G), fast_min_blocks(RUNS, MODE)) st_fast_kernel(const StParams p, const float2 *__restrict__ g_tw,
                                                                 const float2 *__restrict__ g_twp, unsigned int *work_counter)
 {
     using S = FastShape<R1, R2, G>;
-    constexpr int Nc = S::Nc, N = S::N, K = S::K, Kp = S::Kp, ES = S::ES, H = S::H, ZS = S::ZS, NT = S::NT, TPF = S::TPF;
+    constexpr int Nc = S::Nc, N = S::N, K = S::K, Kp = S::Kp, ES = S::ES, H = S::H, ZS = S::ZS, TPF = S::TPF;
+    constexpr int NT = fast_threads(RUNS, MODE, G);      // 32 * G, or six warps in the LEAN=2 build
     constexpr bool LEAN = fast_is_lean(RUNS, MODE);
+    static_assert(NT == S::NT || LEAN, "only the lean feature kernels run with fewer warps than frame slots");
+    static_assert(NT >= S::FftThreads && NT >= 16 * G + 32, "transform threads, and at least one warp next to the dense pass");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int step = p.step;
     // shared-memory layout: all fixed-size arrays sit at compile-time offsets (no address arithmetic to keep
@@ -583,7 +602,7 @@ __global__ void __launch_bounds__(32 * G, fast_min_blocks(RUNS, MODE)) st_fast_k
     short *const raw = reinterpret_cast<short *>(sS + (((G - 1) * step + N + 8) & ~3) + (zs_alias ? 0 : 2 * G * ZS));
     float *Xrows = reinterpret_cast<float *>(E);                             // rows f -> Xrows + f*Kp (aliases E)
     static_assert(size_t(G) * Kp * sizeof(float) <= size_t(G) * R1 * ES * sizeof(float2), "alias");
-    static_assert((G & (G - 1)) == 0 && G * 26 <= NT, "tile mapping");
+    static_assert((G & (G - 1)) == 0, "tile mapping");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if constexpr (!LEAN) {
@@ -810,7 +829,7 @@ __global__ void __launch_bounds__(32 * G, fast_min_blocks(RUNS, MODE)) st_fast_k
             if (rr > G) rr -= G + 1;
             float *fv = fvrows + rr * kFvStride;
             if (warp >= G / 2) {
-                upper_mel_chroma<G, LEAN>(Xrows, Kp, ng, tb, blob_t + p.bl.mel_grp, mscr, chr, tid - NT / 2);
+                upper_mel_chroma<G, LEAN, NT - 16 * G>(Xrows, Kp, ng, tb, blob_t + p.bl.mel_grp, mscr, chr, tid - 16 * G);
             } else {
                 const fidx_t fr = g0 + f;
                 const float *X = Xrows + size_t(f) * Kp;
@@ -824,9 +843,22 @@ __global__ void __launch_bounds__(32 * G, fast_min_blocks(RUNS, MODE)) st_fast_k
             }
             __syncthreads();
             // ---- phase B: DCT rows (all threads), then chroma normalisation (lower half) / time-domain rows (upper half)
-            flat_dct<G, LEAN>(mscr, ng, tb, fvrows, fbase, tid);
+            flat_dct<G, LEAN, NT>(mscr, ng, tb, fvrows, fbase, tid);
             if (warp >= G / 2) {
-                if (RUNS) time_features_runs_h<N>(runE + (f * step) / 8, runF + (f * step) / 8, fv, l16, act);
+                if (RUNS) {
+                    // the NT/32 - G/2 upper warps take the frames two at a time (one round when every frame pair has a warp)
+                    constexpr int UW = NT / 32 - G / 2;
+                    static_assert((G / 2) % UW == 0, "whole rounds over the frame pairs");
+#pragma unroll
+                    for (int rd = 0; rd < (G / 2) / UW; ++rd) {
+                        const int fq2 = 2 * (wv + rd * UW) + half;
+                        const bool act2 = fq2 < ng;
+                        const int f2 = act2 ? fq2 : 0;
+                        int r2 = fbase + 1 + f2;
+                        if (r2 > G) r2 -= G + 1;
+                        time_features_runs_h<N>(runE + (f2 * step) / 8, runF + (f2 * step) / 8, fvrows + r2 * kFvStride, l16, act2);
+                    }
+                }
             } else {
                 chroma_finalize_h(chr + f * 12, fv, l16, act);
             }
@@ -922,7 +954,7 @@ inline int fast_plan_init(int fs, int window, int step, const std::vector<int> &
 template <int R1, int R2, int G, bool EVEN, bool RUNS, int MODE>
 inline int fast_launch_t(const FastTables &ft, StParams p, int sm_count, int64_t T, cudaStream_t st)
 {
-    constexpr int NT = 32 * G;
+    constexpr int NT = fast_threads(RUNS, MODE, G);
     const size_t smem = fast_smem_bytes<R1, R2, G>(p.step, p.bl.words, RUNS, fast_is_lean(RUNS, MODE));
     if (smem > 110u * 1024u) return B200AA_ERR_UNSUPPORTED;      // very large hop: leave it to the generic kernel
     auto kern = st_fast_kernel<R1, R2, G, EVEN, RUNS, MODE>;

@@ -7,7 +7,7 @@ Variants land in pyaudioanalysis_b200/variants/libb200aa_<name>.so (git-ignored 
 GPU box by gpurun) and are selected per process with the B200AA_LIB environment variable.  One gpurun call A/Bs
 them (quick parity against the oracle + kernel timing per build):
 
-    gpurun --timeout 300 -- 'python scripts/ab_run.py default lean mb4 | tee gpurun_out/ab.jsonl'
+    gpurun --timeout 300 -- 'python scripts/ab_run.py default lean lean6 mb4 | tee gpurun_out/ab.jsonl'
 
 and the full suite runs on a variant with `B200AA_LIB=$PWD/pyaudioanalysis_b200/variants/libb200aa_lean.so python -m
 pytest tests -m gpu -q`.
@@ -27,6 +27,9 @@ VARIANTS = {
     # 4 CTAs / SM for the run-staged feature kernels: 64 registers, 56 KB shared memory (tables through L1,
     # one carried |X| row, 16-bit flip words); see B200AA_FAST_LEAN in csrc/fast_kernel.cuh
     "lean": ["-DB200AA_FAST_LEAN=1"],
+    # lean + six-warp CTAs (five transform warps + one spare, dense pass on four warps, mel / chroma on two):
+    # 4 CTAs / SM at 80 registers instead of 64
+    "lean6": ["-DB200AA_FAST_LEAN=2"],
     # 64 registers / 4 CTAs per SM without the diet: only the small-window shapes (<= 45 KB: 320 / 400 / 480-sample
     # windows) actually reach 4 CTAs per SM with it
     "mb4": ["-DB200AA_FAST_MINBLOCKS=4"],
