@@ -21,6 +21,14 @@
 
 using namespace b200aa;
 
+// Experimental (-DB200AA_HOST_PIPELINE=1, scripts/build_variants.py "hostpipe"): b200aa_st_features_host cuts large
+// batches into chunks and queues every chunk's upload, kernels and download on one of three streams, so the PCIe
+// transfers of neighbouring chunks overlap the kernels (what hostpipe.HostPipeline does above the C ABI today).
+// Off by default: not yet run on a B200.
+#ifndef B200AA_HOST_PIPELINE
+#define B200AA_HOST_PIPELINE 0
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // error plumbing
 // ------------------------------------------------------------------------------------------------
@@ -141,10 +149,22 @@ struct b200aa_plan {
     void *ws[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t ws_cap[4] = {0, 0, 0, 0};
     FastTables fast{};                  // extra device tables of the specialised kernel
+#if B200AA_HOST_PIPELINE
+    static constexpr int kPipe = 3;     // streams of the chunked host pipeline, each with its own clips / records / features buffers
+    cudaStream_t pipe_stream[kPipe] = {nullptr, nullptr, nullptr};
+    void *pipe_ws[kPipe][3] = {};
+    size_t pipe_cap[kPipe][3] = {};
+#endif
     ~b200aa_plan()
     {
         if (d_blob) cudaFree(d_blob);
         for (void *w : ws) if (w) cudaFree(w);
+#if B200AA_HOST_PIPELINE
+        for (int k = 0; k < kPipe; ++k) {
+            if (pipe_stream[k]) cudaStreamDestroy(pipe_stream[k]);
+            for (void *w : pipe_ws[k]) if (w) cudaFree(w);
+        }
+#endif
         fast.release();
     }
 };
@@ -773,6 +793,55 @@ struct HostCall {
     }
 };
 
+#if B200AA_HOST_PIPELINE
+// Chunked, multi-stream form of b200aa_st_features_host for batches of many clips (pinned host memory makes the copies
+// truly asynchronous; pageable memory still works, the copies then serialise in the driver).
+static int st_features_host_pipelined(b200aa_plan *pl, const void *h_sig, int dtype, int64_t n_clips, int64_t n_samples,
+                                      int deltas, float *h_out, int64_t T, int64_t chunk)
+{
+    std::lock_guard<std::mutex> hold(pl->host_mu);
+    int rc = plan_device_check(pl);
+    if (rc != B200AA_OK) return rc;
+    const size_t es = dtype == B200AA_DTYPE_I16 ? 2 : 4;
+    const size_t F = deltas ? 68 : 34;
+    const size_t need[3] = {size_t(chunk) * n_samples * es, sizeof(b200aa_clip_norm) * size_t(chunk), size_t(chunk) * F * T * 4};
+    for (int k = 0; k < b200aa_plan::kPipe; ++k) {
+        if (!pl->pipe_stream[k]) CK(cudaStreamCreateWithFlags(&pl->pipe_stream[k], cudaStreamNonBlocking));
+        for (int j = 0; j < 3; ++j)
+            if (pl->pipe_cap[k][j] < need[j]) {
+                if (pl->pipe_ws[k][j]) cudaFree(pl->pipe_ws[k][j]);
+                pl->pipe_ws[k][j] = nullptr;
+                pl->pipe_cap[k][j] = 0;
+                CK(cudaMalloc(&pl->pipe_ws[k][j], need[j]));
+                pl->pipe_cap[k][j] = need[j];
+            }
+    }
+    int64_t c = 0;
+    for (int64_t a = 0; a < n_clips && rc == B200AA_OK; a += chunk, ++c) {
+        const int k = int(c % b200aa_plan::kPipe);
+        const int64_t n = std::min<int64_t>(chunk, n_clips - a);
+        cudaStream_t st = pl->pipe_stream[k];      // stream order also protects the buffers: chunk c + kPipe waits for chunk c
+        void *sig = pl->pipe_ws[k][0];
+        b200aa_clip_norm *norm = static_cast<b200aa_clip_norm *>(pl->pipe_ws[k][1]);
+        float *out = static_cast<float *>(pl->pipe_ws[k][2]);
+        cudaError_t e = cudaMemcpyAsync(sig, static_cast<const char *>(h_sig) + size_t(a) * n_samples * es, size_t(n) * n_samples * es,
+                                        cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync (clips)"); break; }
+        rc = b200aa_clip_stats(sig, dtype, n, n_samples, n_samples, nullptr, norm, st);
+        if (rc != B200AA_OK) break;
+        rc = b200aa_st_features(pl, sig, dtype, n, n_samples, n_samples, nullptr, norm, deltas, out, T, st);
+        if (rc != B200AA_OK) break;
+        e = cudaMemcpyAsync(h_out + size_t(a) * F * T, out, size_t(n) * F * T * 4, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync (features)");
+    }
+    for (int k = 0; k < b200aa_plan::kPipe; ++k) {         // drain every stream, also after an error
+        const cudaError_t e = cudaStreamSynchronize(pl->pipe_stream[k]);
+        if (e != cudaSuccess && rc == B200AA_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
+    }
+    return rc;
+}
+#endif
+
 extern "C" int b200aa_st_features_host(const b200aa_plan *plan, const void *h_sig, int dtype, int64_t n_clips,
                                        int64_t n_samples, int deltas, float *h_out)
 {
@@ -781,6 +850,13 @@ extern "C" int b200aa_st_features_host(const b200aa_plan *plan, const void *h_si
     const int64_t T = b200aa_host::num_frames(n_samples, plan->window, plan->step);
     if (T == 0) return B200AA_ERR_TOO_SHORT;
     if (plan->tables_status != B200AA_OK) return plan->tables_status;
+#if B200AA_HOST_PIPELINE
+    {   // chunks of ~32 MB of samples; batches of fewer than two chunks take the single-stream path below
+        const int64_t chunk = std::max<int64_t>(1, (int64_t(32) << 20) / (n_samples * (dtype == B200AA_DTYPE_I16 ? 2 : 4)));
+        if (n_clips >= 2 * chunk)
+            return st_features_host_pipelined(const_cast<b200aa_plan *>(plan), h_sig, dtype, n_clips, n_samples, deltas, h_out, T, chunk);
+    }
+#endif
     const size_t out_b = size_t(n_clips) * (deltas ? 68 : 34) * T * 4;
     HostCall hc(plan);
     int rc = hc.upload(h_sig, dtype, n_clips, n_samples);

@@ -1,11 +1,12 @@
 """A/B several builds of libb200aa.so in ONE gpurun call: quick parity against the oracle + kernel timing per build.
 
-    python scripts/build_variants.py lean lean6 mb4                       # here (no GPU needed)
-    gpurun --timeout 300 -- 'python scripts/ab_run.py default lean lean6 mb4 | tee gpurun_out/ab.jsonl'
+    python scripts/build_variants.py lean lean6 mb4 hostpipe                       # here (no GPU needed)
+    gpurun --timeout 300 -- 'python scripts/ab_run.py default lean lean6 mb4 hostpipe | tee gpurun_out/ab.jsonl'
 
 Every build runs in its own process (the library is chosen at import time through B200AA_LIB).  Prints one JSON line
 per build: {"lib", "parity_ok", "worst", "kernel_ms" (median of 20 launches, CUDA events around the fused kernel only),
-"frames_per_s", "ctas_per_sm"}.  This is a development tool: bench.py stays the number of record.
+"frames_per_s", "host_call_ms" / "host_call_frames_per_s" (b200aa_st_features_host on pinned host buffers, 1000 clips),
+"host_call_matches_device"}.  This is a development tool: bench.py stays the number of record.
 """
 import json
 import os
@@ -55,6 +56,22 @@ def one():
     res["kernel_ms"] = times[len(times) // 2]
     res["kernel_ms_min"] = times[0]
     res["frames_per_s"] = bench.CLIPS_PER_GPU * bench.FRAMES_PER_CLIP / (res["kernel_ms"] * 1e-3)
+    # ---- end to end through the C ABI's host entry point (pinned host buffers, copies inside the timed region)
+    import ctypes
+    import time
+    h_in = torch.empty((bench.CLIPS_PER_GPU, bench.CLIP_SAMPLES), dtype=torch.int16).pin_memory()
+    h_in.copy_(clips)
+    h_out = torch.empty((bench.CLIPS_PER_GPU, 68, bench.FRAMES_PER_CLIP), dtype=torch.float32).pin_memory()
+    L = pkg._lib.lib()
+    call = lambda: pkg._lib.check(L.b200aa_st_features_host(plan.handle, ctypes.c_void_p(h_in.data_ptr()), 0, bench.CLIPS_PER_GPU,
+                                                            bench.CLIP_SAMPLES, 1, ctypes.c_void_p(h_out.data_ptr())))
+    call()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        call()
+    res["host_call_ms"] = 1e3 * (time.perf_counter() - t0) / 5
+    res["host_call_frames_per_s"] = bench.CLIPS_PER_GPU * bench.FRAMES_PER_CLIP / (res["host_call_ms"] * 1e-3)
+    res["host_call_matches_device"] = bool(torch.equal(h_out[:8], out[:8].cpu()) and torch.equal(h_out[-8:], out[-8:].cpu()))
     print(json.dumps(res), flush=True)
 
 

@@ -7,7 +7,7 @@ Variants land in pyaudioanalysis_b200/variants/libb200aa_<name>.so (git-ignored 
 GPU box by gpurun) and are selected per process with the B200AA_LIB environment variable.  One gpurun call A/Bs
 them (quick parity against the oracle + kernel timing per build):
 
-    gpurun --timeout 300 -- 'python scripts/ab_run.py default lean lean6 mb4 | tee gpurun_out/ab.jsonl'
+    gpurun --timeout 300 -- 'python scripts/ab_run.py default lean lean6 mb4 hostpipe | tee gpurun_out/ab.jsonl'
 
 and the full suite runs on a variant with `B200AA_LIB=$PWD/pyaudioanalysis_b200/variants/libb200aa_lean.so python -m
 pytest tests -m gpu -q`.
@@ -33,6 +33,8 @@ VARIANTS = {
     # 64 registers / 4 CTAs per SM without the diet: only the small-window shapes (<= 45 KB: 320 / 400 / 480-sample
     # windows) actually reach 4 CTAs per SM with it
     "mb4": ["-DB200AA_FAST_MINBLOCKS=4"],
+    # b200aa_st_features_host as a chunked three-stream pipeline below the C ABI (end-to-end through the C entry point)
+    "hostpipe": ["-DB200AA_HOST_PIPELINE=1"],
     # reference points for bisecting: scalar butterflies / IEEE MUFU wrappers
     "nof32x2": ["-DB200AA_NO_F32X2"],
     "noftz": ["-DB200AA_NO_FTZ_MUFU"],
