@@ -5,12 +5,16 @@
 
 Workload (config.workload): BASELINE.json configs[1] -- 1000 synthetic 16 kHz mono int16 10 s clips per
 GPU, window/step 50/25 ms, full 68-row short-term feature matrix.  One "step" = the whole hot path
-over the batch: clip statistics (kernel 0) + fused short-term features (kernel 1), and for N > 1 the
-NCCL gather of every rank's [clips, 68, T] block to rank 0.
-Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the same
-metric through the host-buffer API (pinned host clips in, host features out, copies inside the timed
-region); `roofline` = algorithmic bytes / kernel time of the fused kernel against the measured HBM
-peak; `cpu_baseline` = the oracle's reference-cost port on the host cores (bounded sample).
+over the batch: clip statistics (kernel 0) + fused short-term features (kernel 1); for N > 1 every
+rank's feature kernel stores its [clips, 68, T] block straight into rank 0's peer-mapped gather buffer
+(NVLink, b200aa_peer_buffer_*), i.e. the gather is part of the step (`scaling_detail` also gives the
+step without any gather and with a plain NCCL gather).
+Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the same metric
+through the C ABI's host entry point b200aa_st_features_host (pinned host clips in, pinned host features
+out, copies inside the timed region); `roofline` = algorithmic bytes / kernel time of the fused kernel
+against the measured HBM peak (plus the FP32-issue fraction of the committed ncu capture);
+`cpu_baseline` = the unmodified reference (staged under oracle/_ref by oracle/make_ref.py) on the host
+cores, one single-threaded process per physical core, bounded sample.
 """
 import argparse
 import json
@@ -28,48 +32,120 @@ FRAMES_PER_CLIP = (CLIP_SAMPLES - WINDOW) // STEP + 1            # 399
 ALG_BYTES_PER_CLIP = 2 * CLIP_SAMPLES + 4 * 68 * FRAMES_PER_CLIP   # 428 528
 METRIC = "audio frames/sec short-term feature_extraction @16kHz 50/25ms"
 WORKLOAD = "1000 synthetic 16 kHz mono int16 10 s clips per GPU, win/step 50/25 ms, 68 short-term features (BASELINE configs[1])"
+# identical in both arms (the driver compares the dicts); arm-specific detail goes to `detail`
+CONFIG = {"workload": WORKLOAD, "fs": FS, "window": WINDOW, "step": STEP, "clip_samples": CLIP_SAMPLES,
+          "clips_per_gpu": CLIPS_PER_GPU, "frames_per_clip": FRAMES_PER_CLIP, "n_features": 68,
+          "parallelism": "clips sharded per GPU, feature matrices gathered on rank 0"}
 
 
-# ----------------------------------------------------------------------------- CPU baseline (oracle port)
+# ----------------------------------------------------------------------------- CPU baseline (unmodified reference)
+_PIN_ENV = {"OMP_NUM_THREADS": "1", "MKL_NUM_THREADS": "1", "OPENBLAS_NUM_THREADS": "1", "NUMEXPR_NUM_THREADS": "1",
+            "VECLIB_MAXIMUM_THREADS": "1"}
+_cpu_state = {}
+
+
+def physical_cores():
+    """One logical CPU per physical core among the CPUs this process may run on."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return list(range(os.cpu_count() or 1))
+    seen, out = set(), []
+    for c in allowed:
+        try:
+            with open("/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list" % c) as f:
+                key = f.read().strip()
+        except OSError:
+            key = str(c)
+        if key not in seen:
+            seen.add(key)
+            out.append(c)
+    return out
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def _cpu_init(core_q, kind):
+    """Worker start: one process per physical core, BLAS pools off, the implementation imported once."""
+    os.environ.update(_PIN_ENV)
+    try:
+        os.sched_setaffinity(0, {core_q.get_nowait()})
+    except Exception:
+        pass
+    try:
+        from threadpoolctl import threadpool_limits
+        _cpu_state["tp"] = threadpool_limits(1)
+    except Exception:
+        pass
+    from oracle import st_oracle as O
+    _cpu_state["synth"] = O.synth_clip
+    if kind == "reference":
+        import warnings
+        warnings.simplefilter("ignore")
+        from oracle.ref_import import load_reference
+        S = load_reference(staged_ok=True)[0]
+        _cpu_state["fe"] = lambda x: S.feature_extraction(x, FS, WINDOW, STEP)[0]
+    else:
+        _cpu_state["fe"] = lambda x: O.feature_extraction_loop(x, FS, WINDOW, STEP, deltas=True, tables_per_frame=True)[0]
+
+
 def _cpu_worker(args):
     idx, n_clips = args
-    from oracle import st_oracle as O
     frames = 0
     for i in range(n_clips):
-        x = O.synth_clip(idx * 1000 + i, CLIP_SAMPLES, FS)
-        F, _ = O.feature_extraction_loop(x, FS, WINDOW, STEP, deltas=True, tables_per_frame=True)
-        frames += F.shape[1]
+        x = _cpu_state["synth"](idx * 1000 + i, CLIP_SAMPLES, FS)
+        frames += _cpu_state["fe"](x).shape[1]
     return frames
 
 
-def cpu_baseline(target_seconds=12.0, cores=None, steps=1, warmup=0):
-    """Time the oracle's frame-by-frame port (reference cost profile) on all host cores.
+def cpu_baseline(target_seconds=12.0, steps=1, warmup=0):
+    """Time the reference's own feature_extraction on the host cores.
 
-    `steps` timed passes (after `warmup` untimed ones) over a bounded sample of the workload: every pass runs
-    `per` ten-second clips on each of `cores` processes, `per` chosen from a one-clip probe so that the timed
-    passes together take about `target_seconds`.  Returns (cpu_baseline dict, frames, seconds) over the timed passes.
+    `steps` timed passes (after `warmup` untimed ones) over a bounded sample of the workload: every pass runs `per`
+    ten-second clips on each of `cores` single-threaded processes (one per physical core), `per` chosen from a
+    one-clip probe so that the timed passes together take about `target_seconds`.
+    Returns (cpu_baseline dict, frames, seconds) over the timed passes.
     """
-    cores = cores or os.cpu_count() or 1
-    cores = min(cores, 64)
+    from oracle.ref_import import reference_available, staged_available
+    kind = "reference" if (staged_available() or reference_available()) else "port"
+    cores = physical_cores()
+    if len(cores) > 128:
+        cores = cores[:128]
+    n = len(cores)
+    os.environ.update(_PIN_ENV)            # inherited by the spawned workers before NumPy loads its BLAS
     ctx = mp.get_context("spawn")
-    with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(900 + c, 0) for c in range(cores)])          # start workers / import
+    q = ctx.Queue()
+    for c in cores:
+        q.put(c)
+    with ctx.Pool(n, initializer=_cpu_init, initargs=(q, kind)) as pool:
+        pool.map(_cpu_worker, [(900 + c, 0) for c in range(n)], chunksize=1)      # start workers / import
         t0 = time.perf_counter()
-        pool.map(_cpu_worker, [(c, 1) for c in range(cores)])                # probe: one clip per worker
+        pool.map(_cpu_worker, [(c, 1) for c in range(n)], chunksize=1)            # probe: one clip per worker (also warm-up)
         probe = time.perf_counter() - t0
         per = max(1, int(target_seconds / max(steps, 1) / max(probe, 1e-3)))
         per = min(per, 32)
         for w in range(warmup):
-            pool.map(_cpu_worker, [(5000 + 64 * w + c, 1) for c in range(cores)])
+            pool.map(_cpu_worker, [(5000 + 64 * w + c, 1) for c in range(n)], chunksize=1)
         frames, dt = 0, 0.0
         for k in range(max(steps, 1)):
             t0 = time.perf_counter()
-            frames += sum(pool.map(_cpu_worker, [(100 + 64 * k + c, per) for c in range(cores)]))
+            frames += sum(pool.map(_cpu_worker, [(100 + 64 * k + c, per) for c in range(n)], chunksize=1))
             dt += time.perf_counter() - t0
-    return {"value": frames / dt, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": "%d pass(es) of %d clips of 10 s (%d frames in all) on %d processes, oracle.feature_extraction_loop "
-                      "(per-frame loop incl. the reference's per-frame chroma-table rebuild), %.1f s wall"
-                      % (max(steps, 1), per * cores, frames, cores, dt)}, frames, dt
+    what = ("the unmodified reference ShortTermFeatures.feature_extraction (oracle/_ref, staged by oracle/make_ref.py)"
+            if kind == "reference" else "oracle.feature_extraction_loop (port with the reference's cost profile)")
+    return {"value": frames / dt, "unit": "frames/s", "cores": n, "kind": kind, "cpu": cpu_model(),
+            "threads_per_process": 1,
+            "sample": "%d pass(es) of %d clips of 10 s (%d frames in all), one single-threaded process pinned to each of %d "
+                      "physical cores, %s, %.1f s wall" % (max(steps, 1), per * n, frames, n, what, dt)}, frames, dt
 
 
 # ----------------------------------------------------------------------------- clocks sampler
@@ -127,6 +203,17 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_facts():
+    """Figures of the committed `ncu --set full` capture of the fused kernel (profiles/traffic.json): DRAM bytes per
+    launch, warp instructions per launch, issue-slot utilisation.  Static by nature (a profiler cannot run inside
+    the timed region); the file names the capture they come from."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 # ----------------------------------------------------------------------------- reference arm
 def run_reference(args, rank, world):
     if rank != 0:
@@ -135,9 +222,9 @@ def run_reference(args, rank, world):
     cb, frames, dt = cpu_baseline(target_seconds=30.0, steps=steps, warmup=min(args.warmup, 3))
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "frames/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU reference arm: the reference is pure Python and cannot travel to the "
-                       "GPU box; this is the oracle's frame-by-frame port with the reference's cost profile, all host cores"},
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": CONFIG,
+            "detail": "CPU arm: each step is a bounded sample of the workload (see cpu_baseline.sample); a rate on identical "
+                      "clips and parameters",
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -164,11 +251,14 @@ def synth_device_batch(torch, n_clips, seed, device):
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
+    from pyaudioanalysis_b200 import numa
+    bound = numa.bind_to_gpu(local_rank)         # before any pinned allocation: staging buffers on the GPU's NUMA node
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     import pyaudioanalysis_b200 as pkg
     from pyaudioanalysis_b200 import _lib
     from pyaudioanalysis_b200.hostpipe import HostPipeline
+    from pyaudioanalysis_b200.dist import PeerGather
     L = _lib.lib()
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -177,104 +267,108 @@ def run_ours(args, rank, world, local_rank):
     clips = synth_device_batch(torch, B, 1234 + rank, dev)
     plan = _lib.get_plan(FS, WINDOW, STEP, local_rank)
     T = FRAMES_PER_CLIP
-    out = torch.empty((B, 68, T), dtype=torch.float32, device=dev)
-    # N > 1: rank 0 receives every rank's [B, 68, T] block.  The NCCL gather of step i runs asynchronously
-    # (NCCL's own stream) while the kernels of step i+1 execute; outputs are double-buffered so a buffer is
-    # only overwritten after its gather completed.  Every gather is waited for before the clock stops.
-    outs = [out, torch.empty_like(out)] if world > 1 else [out]
-    gathered = [torch.empty((world, B, 68, T), dtype=torch.float32, device=dev) for _ in range(2)] \
-        if (world > 1 and rank == 0) else None
-    pending = [None, None]
+    local_out = torch.empty((B, 68, T), dtype=torch.float32, device=dev)
+    # N > 1: rank 0 owns a [world*B, 68, T] buffer that every rank maps over NVLink; a rank's kernel writes its block
+    # straight into it (double-buffered per step parity so that step i+1 never overwrites what the root may still read)
+    gathers = [PeerGather(world * B, 68, T, dst=0) for _ in range(2)] if world > 1 else None
+    nccl_dst = [torch.empty((world, B, 68, T), dtype=torch.float32, device=dev)] if (world > 1 and rank == 0) else None
 
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-    k_start, k_end = [ev() for _ in range(args.steps)], [ev() for _ in range(args.steps)]
-    counter = [0]
+    ev = lambda: torch.cuda.Event(enable_timing=True)     # noqa: E731
 
-    def step(i=None, collective=True):
-        slot = counter[0] % len(outs)
-        counter[0] += 1
-        if world > 1 and pending[slot] is not None:
-            pending[slot].wait()                      # the buffer's previous gather must be done
-            pending[slot] = None
-        norm = pkg.clip_stats(clips)
-        if i is not None:
-            k_start[i].record()
-        pkg.feature_extraction_batch(clips, FS, WINDOW, STEP, deltas=True, out=outs[slot], norm=norm, plan=plan)
-        if i is not None:
-            k_end[i].record()
-        if world > 1 and collective:
-            dst_list = [gathered[slot][r] for r in range(world)] if rank == 0 else None
-            pending[slot] = dist.gather(outs[slot], dst_list, dst=0, async_op=True)
-
-    def drain():
-        for k in range(len(pending)):
-            if pending[k] is not None:
-                pending[k].wait()
-                pending[k] = None
-
-    for _ in range(max(3, args.warmup)):
-        step()
-    drain()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    launches0 = L.b200aa_launch_count()
-    e0, e1 = ev(), ev()
-    with ClockSampler(local_rank) as clk:
-        e0.record()
-        for i in range(args.steps):
-            step(i)
-        drain()
-        e1.record()
-        launches = L.b200aa_launch_count() - launches0          # our kernels launched inside the timed region
+    def timed(mode, steps, record_kernel=False):
+        """`steps` passes in gather mode `mode` ('p2p' | 'none' | 'nccl'); returns (ms total max over ranks, kernel ms)."""
+        ks, ke = [ev() for _ in range(steps)], [ev() for _ in range(steps)]
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for i in range(steps):
+            norm = pkg.clip_stats(clips)
+            out = gathers[i % 2].view(rank * B, (rank + 1) * B) if (mode == "p2p" and world > 1) else local_out
+            ks[i].record()
+            pkg.feature_extraction_batch(clips, FS, WINDOW, STEP, deltas=True, out=out, norm=norm, plan=plan)
+            ke[i].record()
+            if mode == "nccl" and world > 1:
+                dist.gather(local_out, [nccl_dst[0][r] for r in range(world)] if rank == 0 else None, dst=0)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()          # all ranks' remote stores have landed before the clock is read
+        ms = e0.elapsed_time(e1)
+        kms = sum(a.elapsed_time(b) for a, b in zip(ks, ke)) / steps
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), kms
+
+    main_mode = "p2p" if world > 1 else "none"
+    timed(main_mode, max(3, args.warmup))
+    launches0 = L.b200aa_launch_count()
+    with ClockSampler(local_rank) as clk:
+        ms_total, kernel_ms = timed(main_mode, args.steps)
+        launches = L.b200aa_launch_count() - launches0          # our kernels launched inside the timed region
         # keep the sampler alive for a few more identical steps if the timed region was very short
         t_end = time.time() + 0.25
         while time.time() < t_end and len(clk.samples) < 8:
-            step(collective=False)       # local work only: the iteration count differs between ranks
+            pkg.feature_extraction_batch(clips, FS, WINDOW, STEP, deltas=True, out=local_out, plan=plan)
             torch.cuda.synchronize()
-    ms_total = e0.elapsed_time(e1)
-    kernel_ms = sum(a.elapsed_time(b) for a, b in zip(k_start, k_end)) / args.steps
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
     frames_per_step = world * B * T
     value = frames_per_step / (ms_per_step * 1e-3)
+    scaling_detail = None
+    if world > 1:
+        timed("none", 3)
+        ms_none, _ = timed("none", args.steps)
+        timed("nccl", 3)
+        ms_nccl, _ = timed("nccl", args.steps)
+        gather_bytes = (world - 1) * B * 68 * T * 4
+        scaling_detail = {"gather": "fused: every rank's feature kernel stores its block into rank 0's peer-mapped buffer (NVLink)",
+                          "frames_per_s_with_fused_gather": value,
+                          "frames_per_s_without_gather": frames_per_step / (ms_none / args.steps * 1e-3),
+                          "frames_per_s_with_nccl_gather": frames_per_step / (ms_nccl / args.steps * 1e-3),
+                          "ms_per_step": {"fused_gather": ms_per_step, "no_gather": ms_none / args.steps, "nccl_gather": ms_nccl / args.steps},
+                          "root_ingress_bytes_per_step": gather_bytes,
+                          "root_ingress_GBps_fused": gather_bytes / (ms_per_step * 1e-3) / 1e9,
+                          "limiter": "root NVLink ingress (7 blocks of 108.5 MB per step at N=8 against ~770 GB/s measured per direction)"}
+        # the gathered tensor on the root holds every rank's block (spot check against the local result)
+        if rank == 0:
+            full = gathers[(args.steps - 1) % 2].view(0, world * B)
+            pkg.feature_extraction_batch(clips, FS, WINDOW, STEP, deltas=True, out=local_out, plan=plan)
+            torch.cuda.synchronize()
+            assert torch.equal(full[:B], local_out), "gather buffer does not hold rank 0's block"
+            assert torch.isfinite(full[(world - 1) * B:]).all() and full[(world - 1) * B:, 1].abs().sum() > 0, "last rank's block missing"
 
-    # ---- end to end through the public host API: pinned host clips -> host features
+    # ---- end to end through the C ABI host entry point: pinned host clips -> pinned host features
     e2e = None
-    if (rank == 0 or world > 1) and not args.no_e2e:
-        host_in = torch.empty((B, CLIP_SAMPLES), dtype=torch.int16).pin_memory()
-        host_in.copy_(clips)
-        pipe = HostPipeline(FS, WINDOW, STEP, CLIP_SAMPLES, max_clips=B, device=local_rank)
-        host_out = pipe.run(host_in)           # warm-up (allocations, plan)
+    if not args.no_e2e:
+        pipe = HostPipeline(FS, WINDOW, STEP, CLIP_SAMPLES, max_clips=B, device=local_rank, bind_numa=False)
+        pipe.h_in[:] = clips.cpu().numpy()
+        host_out = pipe.run()                  # warm-up (allocations, plan)
         for _ in range(2):
-            pipe.run(host_in)
+            pipe.run()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         n_e2e = max(3, min(args.steps, 10))
         t0 = time.perf_counter()
         for _ in range(n_e2e):
-            host_out = pipe.run(host_in)
-        torch.cuda.synchronize()
+            host_out = pipe.run()
         dt = (time.perf_counter() - t0) / n_e2e
         td = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(td, op=dist.ReduceOp.MAX)
         dt = float(td.item())
-        e2e = {"value": frames_per_step / dt, "unit": "frames/s", "h2d_bytes_per_step": int(host_in.numel() * 2),
-               "d2h_bytes_per_step": int(host_out.numel() * 4), "ms_per_step": 1e3 * dt,
-               "api": "pyaudioanalysis_b200.hostpipe.HostPipeline.run (pinned host int16 in, pinned host float32 out, chunked "
-                      "H2D / b200aa_clip_stats + b200aa_st_features / D2H round-robin on three streams)"}
+        e2e = {"value": frames_per_step / dt, "unit": "frames/s", "h2d_bytes_per_step": int(pipe.h_in.nbytes),
+               "d2h_bytes_per_step": int(host_out.nbytes), "ms_per_step": 1e3 * dt,
+               "api": "b200aa_st_features_host (C ABI via ctypes; pinned host int16 in, pinned host float32 out; inside: ~32 MB "
+                      "chunks, H2D / b200aa_clip_stats + b200aa_st_features / D2H round-robin on three streams)",
+               "numa": bound}
         # parity spot check of the e2e result against the device-resident result
-        assert torch.equal(host_out[:4], out[:4].cpu()), "host pipeline and device path disagree"
+        pkg.feature_extraction_batch(clips, FS, WINDOW, STEP, deltas=True, out=local_out, plan=plan)
+        torch.cuda.synchronize()
+        assert (host_out[:4] == local_out[:4].cpu().numpy()).all(), "host entry point and device path disagree"
 
     if rank != 0:
         if world > 1:
@@ -283,25 +377,29 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = hbm_peak()
     alg_bytes = B * ALG_BYTES_PER_CLIP
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("st_kernel_dram_bytes_per_launch")
-    except Exception:
-        pass
+    nf = ncu_facts()
+    inst = nf.get("st_kernel_warp_instructions_per_launch")
+    sm_clock_hz = 1e6 * (clk.summary()["sm_mhz"] or 1965)
+    issue_frac = (inst / (kernel_ms * 1e-3) / (148 * 4 * sm_clock_hz)) if inst else None
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "impl": "ours",
-            "config": {"workload": WORKLOAD, "clips_per_gpu": B, "frames_per_clip": T, "parallelism": "clips sharded per GPU" +
-                       (", async NCCL gather of every rank's [clips,68,T] block to rank 0 per step (double-buffered: the gather of step i overlaps the kernels of step i+1; all gathers complete inside the timed region)" if world > 1 else ""),
-                       "l2": "inputs larger than L2 (320 MB int16 clips + 108 MB output per step vs 126 MB L2); no explicit flush",
-                       "kernel_kind": plan.kernel_kind(),
+            "data": "synthetic", "impl": "ours", "config": CONFIG,
+            "detail": {"l2": "inputs larger than L2 (320 MB int16 clips + 108 MB output per step vs 126 MB L2); no explicit flush",
+                       "kernel_kind": plan.kernel_kind(), "numa": bound,
                        **({"lib_override": os.environ["B200AA_LIB"]} if os.environ.get("B200AA_LIB") else {})},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "fused short-term feature kernel",
+                         "traffic": nf.get("st_kernel_dram_bytes_per_launch"), "traffic_source": nf.get("source"),
+                         "peak_source": peak_src, "kernel": "fused short-term feature kernel",
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "kernel is FP32-issue bound, not HBM bound (DESIGN.md): ~30 kFLOP per 1074 B frame"},
+                         "binding_bound": "fp32_issue",
+                         "fp32_issue_frac": issue_frac, "inst_per_frame": (inst / (B * T)) if inst else None,
+                         "issue_slot_utilisation_ncu": nf.get("st_kernel_issue_slot_utilisation"),
+                         "note": "the kernel is instruction-issue bound, not HBM bound (DESIGN.md): ~30 kFLOP per 1074 B frame; "
+                                 "fp32_issue_frac = warp instructions per launch (ncu capture) / kernel time / (148 SMs x 4 "
+                                 "schedulers x SM clock)"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches)}
+    if scaling_detail:
+        line["scaling_detail"] = scaling_detail
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"], _, _ = cpu_baseline(target_seconds=30.0)
     print(json.dumps(line), flush=True)

@@ -16,6 +16,7 @@
 #ifndef B200AA_H_
 #define B200AA_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -144,6 +145,23 @@ int b200aa_chromagram_host(const b200aa_plan *plan, const void *h_sig, int dtype
 int b200aa_mid_features_host(const b200aa_plan *plan, const void *h_sig, int dtype, int64_t n_samples,
                              int ratio, int step_ratio,
                              float *h_mid /* [136, M] */, float *h_st /* [68, T], nullable */);
+
+/* Pinned (page-locked) host buffers for the host entry points: with them the chunked pipeline inside
+ * b200aa_st_features_host overlaps the PCIe copies of neighbouring chunks with the kernels.  Pages are placed by
+ * the calling thread's NUMA policy -- bind the thread to the GPU's node first (pyaudioanalysis_b200/numa.py).
+ * Replaces nothing in the reference (its arrays are pageable NumPy buffers, audioBasicIO.py:86-110); SURVEY 8f rank 2. */
+int b200aa_host_alloc(void **h_out, size_t bytes);
+int b200aa_host_free(void *h_ptr);
+
+/* Peer-mapped gather target (BASELINE configs[4]): the root rank creates one device buffer for the
+ * features of ALL clips and exports a 64-byte handle; every other rank of the box opens it (CUDA IPC, NVLink peer
+ * mapping) and passes `peer_ptr + its slice offset` as d_out of b200aa_st_features, so the tile stores of the
+ * fused kernel land in the root's HBM: the gather needs no collective kernel and no SMs on the root.  Handles
+ * travel between the processes by any byte channel (the Python host side uses torch.distributed). */
+#define B200AA_IPC_HANDLE_BYTES 64
+int b200aa_peer_buffer_create(size_t bytes, void **d_out, unsigned char *handle_out /* [64] */);
+int b200aa_peer_buffer_open(const unsigned char *handle /* [64] */, void **d_out);
+int b200aa_peer_buffer_close(void *d_ptr, int owner /* 1: the creating rank (frees), 0: a mapping rank (unmaps) */);
 
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t b200aa_launch_count(void);

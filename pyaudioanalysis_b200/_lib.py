@@ -46,6 +46,11 @@ SIGNATURES = {
     "b200aa_spectrogram_host": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp]),
     "b200aa_chromagram_host": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp]),
     "b200aa_mid_features_host": (c_int, [c_vp, c_vp, c_int, c_i64, c_int, c_int, c_vp, c_vp]),
+    "b200aa_host_alloc": (c_int, [ctypes.POINTER(c_vp), ctypes.c_size_t]),
+    "b200aa_host_free": (c_int, [c_vp]),
+    "b200aa_peer_buffer_create": (c_int, [ctypes.c_size_t, ctypes.POINTER(c_vp), c_vp]),
+    "b200aa_peer_buffer_open": (c_int, [c_vp, ctypes.POINTER(c_vp)]),
+    "b200aa_peer_buffer_close": (c_int, [c_vp, c_int]),
     "b200aa_launch_count": (c_i64, []),
 }
 

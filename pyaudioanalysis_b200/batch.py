@@ -13,6 +13,17 @@ from ._lib import lib, check, get_plan, DTYPE_I16, DTYPE_F32
 NORM_BYTES = 32
 
 
+class DeviceBuffer:
+    """Raw float32 device memory [shape] given by address -- e.g. a window of another GPU's HBM mapped over NVLink
+    (dist.PeerGather).  Accepted as ``out=`` of feature_extraction_batch; the caller guarantees size and lifetime."""
+
+    def __init__(self, ptr, shape):
+        self.ptr, self.shape, self.is_cuda = int(ptr), tuple(int(s) for s in shape), True
+
+    def data_ptr(self):
+        return self.ptr
+
+
 def _require_cuda(t, name):
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise TypeError("%s must be a CUDA tensor (there is no CPU fallback)" % name)
@@ -79,6 +90,9 @@ def feature_extraction_batch(signals, sampling_rate, window, step, deltas=True, 
         if out is None:
             alloc = torch.zeros if lengths is not None else torch.empty
             out = alloc((B, F, T), dtype=torch.float32, device=signals.device)
+        elif isinstance(out, DeviceBuffer):
+            if out.shape[0] != B or out.shape[1] != F or out.shape[2] < T:
+                raise ValueError("out must be float32 [B, %d, >=%d]" % (F, T))
         else:
             _require_cuda(out, "out")
             if out.dtype != torch.float32 or out.shape[0] != B or out.shape[1] != F or out.shape[2] < T or not out.is_contiguous():

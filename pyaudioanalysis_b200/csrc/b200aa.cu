@@ -21,14 +21,6 @@
 
 using namespace b200aa;
 
-// Experimental (-DB200AA_HOST_PIPELINE=1, scripts/build_variants.py "hostpipe"): b200aa_st_features_host cuts large
-// batches into chunks and queues every chunk's upload, kernels and download on one of three streams, so the PCIe
-// transfers of neighbouring chunks overlap the kernels (what hostpipe.HostPipeline does above the C ABI today).
-// Off by default: not yet run on a B200.
-#ifndef B200AA_HOST_PIPELINE
-#define B200AA_HOST_PIPELINE 0
-#endif
-
 // ------------------------------------------------------------------------------------------------
 // error plumbing
 // ------------------------------------------------------------------------------------------------
@@ -149,22 +141,18 @@ struct b200aa_plan {
     void *ws[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t ws_cap[4] = {0, 0, 0, 0};
     FastTables fast{};                  // extra device tables of the specialised kernel
-#if B200AA_HOST_PIPELINE
     static constexpr int kPipe = 3;     // streams of the chunked host pipeline, each with its own clips / records / features buffers
     cudaStream_t pipe_stream[kPipe] = {nullptr, nullptr, nullptr};
     void *pipe_ws[kPipe][3] = {};
     size_t pipe_cap[kPipe][3] = {};
-#endif
     ~b200aa_plan()
     {
         if (d_blob) cudaFree(d_blob);
         for (void *w : ws) if (w) cudaFree(w);
-#if B200AA_HOST_PIPELINE
         for (int k = 0; k < kPipe; ++k) {
             if (pipe_stream[k]) cudaStreamDestroy(pipe_stream[k]);
             for (void *w : pipe_ws[k]) if (w) cudaFree(w);
         }
-#endif
         fast.release();
     }
 };
@@ -793,9 +781,10 @@ struct HostCall {
     }
 };
 
-#if B200AA_HOST_PIPELINE
-// Chunked, multi-stream form of b200aa_st_features_host for batches of many clips (pinned host memory makes the copies
-// truly asynchronous; pageable memory still works, the copies then serialise in the driver).
+// Chunked, multi-stream form of b200aa_st_features_host for batches of many clips: every chunk's upload, kernels and
+// download are queued on one of three streams, so the PCIe transfers of neighbouring chunks overlap the kernels (pinned
+// host memory -- b200aa_host_alloc -- makes the copies truly asynchronous; pageable memory still works, the copies
+// then serialise in the driver).
 static int st_features_host_pipelined(b200aa_plan *pl, const void *h_sig, int dtype, int64_t n_clips, int64_t n_samples,
                                       int deltas, float *h_out, int64_t T, int64_t chunk)
 {
@@ -840,7 +829,6 @@ static int st_features_host_pipelined(b200aa_plan *pl, const void *h_sig, int dt
     }
     return rc;
 }
-#endif
 
 extern "C" int b200aa_st_features_host(const b200aa_plan *plan, const void *h_sig, int dtype, int64_t n_clips,
                                        int64_t n_samples, int deltas, float *h_out)
@@ -850,13 +838,11 @@ extern "C" int b200aa_st_features_host(const b200aa_plan *plan, const void *h_si
     const int64_t T = b200aa_host::num_frames(n_samples, plan->window, plan->step);
     if (T == 0) return B200AA_ERR_TOO_SHORT;
     if (plan->tables_status != B200AA_OK) return plan->tables_status;
-#if B200AA_HOST_PIPELINE
     {   // chunks of ~32 MB of samples; batches of fewer than two chunks take the single-stream path below
         const int64_t chunk = std::max<int64_t>(1, (int64_t(32) << 20) / (n_samples * (dtype == B200AA_DTYPE_I16 ? 2 : 4)));
         if (n_clips >= 2 * chunk)
             return st_features_host_pipelined(const_cast<b200aa_plan *>(plan), h_sig, dtype, n_clips, n_samples, deltas, h_out, T, chunk);
     }
-#endif
     const size_t out_b = size_t(n_clips) * (deltas ? 68 : 34) * T * 4;
     HostCall hc(plan);
     int rc = hc.upload(h_sig, dtype, n_clips, n_samples);
@@ -926,4 +912,54 @@ extern "C" int b200aa_mid_features_host(const b200aa_plan *plan, const void *h_s
     if ((rc = hc.download(h_mid, mid, mid_b))) return rc;
     if (h_st && (rc = hc.download(h_st, stf, st_b))) return rc;
     return hc.finish();
+}
+
+// ------------------------------------------------------------------------------------------------
+// pinned host buffers (full-speed, truly asynchronous H2D / D2H copies for the host entry points)
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200aa_host_alloc(void **h_out, size_t bytes)
+{
+    if (!h_out) return B200AA_ERR_INVALID;
+    *h_out = nullptr;
+    if (bytes == 0) return B200AA_OK;
+    // pages are placed by the calling thread's NUMA policy: bind the thread to the GPU's node first
+    CK(cudaHostAlloc(h_out, bytes, cudaHostAllocPortable));
+    return B200AA_OK;
+}
+extern "C" int b200aa_host_free(void *h_ptr)
+{
+    if (h_ptr) CK(cudaFreeHost(h_ptr));
+    return B200AA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// peer-mapped gather target: rank 0 owns one [n_clips_total, F, T] buffer, every other rank of the
+// box maps it (CUDA IPC over NVLink) and its feature kernel stores straight into its slice -- the gather is
+// fused into the tile store, no collective kernel, no SMs on the root.
+// ------------------------------------------------------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == B200AA_IPC_HANDLE_BYTES, "handle size");
+extern "C" int b200aa_peer_buffer_create(size_t bytes, void **d_out, unsigned char *handle_out)
+{
+    if (!d_out || !handle_out || bytes == 0) return B200AA_ERR_INVALID;
+    CK(cudaMalloc(d_out, bytes));
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, *d_out);
+    if (e != cudaSuccess) { cudaFree(*d_out); *d_out = nullptr; return cuda_fail(e, "cudaIpcGetMemHandle"); }
+    std::memcpy(handle_out, &h, sizeof(h));
+    return B200AA_OK;
+}
+extern "C" int b200aa_peer_buffer_open(const unsigned char *handle, void **d_out)
+{
+    if (!handle || !d_out) return B200AA_ERR_INVALID;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    CK(cudaIpcOpenMemHandle(d_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return B200AA_OK;
+}
+extern "C" int b200aa_peer_buffer_close(void *d_ptr, int owner)
+{
+    if (!d_ptr) return B200AA_OK;
+    if (owner) CK(cudaFree(d_ptr));
+    else CK(cudaIpcCloseMemHandle(d_ptr));
+    return B200AA_OK;
 }

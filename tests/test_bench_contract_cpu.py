@@ -1,9 +1,11 @@
-"""CPU: the reference arm of bench.py (`--impl reference`, the oracle port on the host cores) prints one JSON line
-with the keys the driver reads."""
+"""CPU: the reference arm of bench.py (`--impl reference`: the staged unmodified reference -- or the oracle port when
+oracle/_ref is absent -- on the host cores) prints one JSON line with the keys the driver reads."""
 import json
 import os
 import subprocess
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -21,6 +23,11 @@ def test_reference_arm_json_line():
         assert key in j, key
     assert j["vs_baseline"] is None and j["value"] > 0
     cb = j["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == j["value"] and "clips" in cb["sample"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == j["value"] and "clips" in cb["sample"]
+    if os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "pyAudioAnalysis")):
+        assert cb["kind"] == "reference"          # the staged unmodified reference is what gets timed when present
+    assert cb["threads_per_process"] == 1 and cb["cpu"]
+    import bench
+    assert j["config"] == bench.CONFIG           # both arms print the identical config dict
     assert j["e2e"] == {"value": j["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in j["config"]

@@ -261,17 +261,31 @@ def test_file_wrappers(P, tmp_path):
 
 
 def test_host_pipeline(P):
-    """Pinned-host batch API (chunked copies + kernels on several streams) equals the device-resident path."""
+    """Pinned-host batch API = one call of the C ABI's b200aa_st_features_host (chunked copies + kernels on three
+    streams inside the library for big batches, single stream for small ones) equals the device-resident path."""
     import torch
     from pyaudioanalysis_b200.hostpipe import HostPipeline
     clips = np.stack([O.synth_clip(200 + i, 16000, 16000) for i in range(7)])
-    host = torch.from_numpy(clips).pin_memory()
-    pipe = HostPipeline(16000, 800, 400, 16000, max_clips=7, device=0, chunk_clips=3, n_streams=2)
-    got = pipe.run(host).clone()
-    ref = P.feature_extraction_batch(torch.from_numpy(clips).cuda(), 16000, 800, 400).cpu()
-    assert torch.equal(got, ref)
-    again = pipe.run(host[:4])
-    assert torch.equal(again, ref[:4])
+    pipe = HostPipeline(16000, 800, 400, 16000, max_clips=7, device=0)
+    pipe.h_in[:] = clips
+    got = pipe.run().copy()
+    ref = P.feature_extraction_batch(torch.from_numpy(clips).cuda(), 16000, 800, 400).cpu().numpy()
+    assert (got == ref).all()
+    again = pipe.run(clips[:4])                       # pageable input works too
+    assert (again == ref[:4]).all()
+    with pytest.raises(TypeError):
+        pipe.run(clips.astype(np.float32))            # no silent dtype conversion
+    with pytest.raises(ValueError):
+        pipe.run(clips[:, :8000])
+    # a batch large enough for the chunked three-stream form (> 2 chunks of ~32 MB): 250 clips of 10 s
+    big = np.stack([O.synth_clip(900 + (i % 5), 160000, 16000) for i in range(250)])
+    big[5:] = np.roll(big[5:], 7, axis=1)
+    pipe2 = HostPipeline(16000, 800, 400, 160000, max_clips=250, device=0)
+    pipe2.h_in[:] = big
+    got2 = pipe2.run()
+    ref2 = P.feature_extraction_batch(torch.from_numpy(big).cuda(), 16000, 800, 400).cpu().numpy()
+    assert (got2 == ref2).all()
+    check_features(got2[3], O.feature_extraction(big[3], 16000, 800, 400)[0], 400, "chunked host pipeline clip 3")
 
 
 def test_mid_pool_kernel(P):
