@@ -63,6 +63,24 @@ def physical_cores():
     return out
 
 
+def cpu_quota():
+    """CPUs' worth of time the container may use per period (cgroup v2 cpu.max / v1 cfs quota), or None if unlimited."""
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            q, p = f.read().split()
+            return None if q == "max" else float(q) / float(p)
+    except (OSError, ValueError):
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:
+            q = float(f.read())
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+            p = float(f.read())
+        return None if q <= 0 else q / p
+    except (OSError, ValueError):
+        return None
+
+
 def cpu_model():
     try:
         with open("/proc/cpuinfo") as f:
@@ -87,7 +105,7 @@ def _cpu_init(core_q, kind):
     except Exception:
         pass
     from oracle import st_oracle as O
-    _cpu_state["synth"] = O.synth_clip
+    _cpu_state["clips"] = [O.synth_clip(1000 * (os.getpid() % 977) + i, CLIP_SAMPLES, FS) for i in range(4)]   # outside the timed work
     if kind == "reference":
         import warnings
         warnings.simplefilter("ignore")
@@ -102,8 +120,7 @@ def _cpu_worker(args):
     idx, n_clips = args
     frames = 0
     for i in range(n_clips):
-        x = _cpu_state["synth"](idx * 1000 + i, CLIP_SAMPLES, FS)
-        frames += _cpu_state["fe"](x).shape[1]
+        frames += _cpu_state["fe"](_cpu_state["clips"][(idx + i) % 4]).shape[1]
     return frames
 
 
@@ -118,6 +135,9 @@ def cpu_baseline(target_seconds=12.0, steps=1, warmup=0):
     from oracle.ref_import import reference_available, staged_available
     kind = "reference" if (staged_available() or reference_available()) else "port"
     cores = physical_cores()
+    quota = cpu_quota()
+    if quota is not None and quota < len(cores):          # a throttled container: more processes than CPUs only add noise
+        cores = cores[:max(1, int(quota))]
     if len(cores) > 128:
         cores = cores[:128]
     n = len(cores)
@@ -128,6 +148,9 @@ def cpu_baseline(target_seconds=12.0, steps=1, warmup=0):
         q.put(c)
     with ctx.Pool(n, initializer=_cpu_init, initargs=(q, kind)) as pool:
         pool.map(_cpu_worker, [(900 + c, 0) for c in range(n)], chunksize=1)      # start workers / import
+        pool.apply(_cpu_worker, ((7, 1),))                                        # one clip on one process, the others idle:
+        t0 = time.perf_counter()                                                  # the per-core rate without any contention
+        single = pool.apply(_cpu_worker, ((8, 2),)) / (time.perf_counter() - t0)
         t0 = time.perf_counter()
         pool.map(_cpu_worker, [(c, 1) for c in range(n)], chunksize=1)            # probe: one clip per worker (also warm-up)
         probe = time.perf_counter() - t0
@@ -143,7 +166,8 @@ def cpu_baseline(target_seconds=12.0, steps=1, warmup=0):
     what = ("the unmodified reference ShortTermFeatures.feature_extraction (oracle/_ref, staged by oracle/make_ref.py)"
             if kind == "reference" else "oracle.feature_extraction_loop (port with the reference's cost profile)")
     return {"value": frames / dt, "unit": "frames/s", "cores": n, "kind": kind, "cpu": cpu_model(),
-            "threads_per_process": 1,
+            "threads_per_process": 1, "single_process_frames_per_s": single, "cgroup_cpu_quota": quota,
+            "load_avg_1min": (os.getloadavg()[0] if hasattr(os, "getloadavg") else None),
             "sample": "%d pass(es) of %d clips of 10 s (%d frames in all), one single-threaded process pinned to each of %d "
                       "physical cores, %s, %.1f s wall" % (max(steps, 1), per * n, frames, n, what, dt)}, frames, dt
 
@@ -252,6 +276,10 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from pyaudioanalysis_b200 import numa
+    try:
+        full_affinity = os.sched_getaffinity(0)
+    except AttributeError:
+        full_affinity = None
     bound = numa.bind_to_gpu(local_rank)         # before any pinned allocation: staging buffers on the GPU's NUMA node
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -401,6 +429,8 @@ def run_ours(args, rank, world, local_rank):
     if scaling_detail:
         line["scaling_detail"] = scaling_detail
     if world == 1 and not args.no_cpu:
+        if full_affinity is not None:
+            os.sched_setaffinity(0, full_affinity)       # the CPU baseline uses every core of the box, not only the GPU's node
         line["cpu_baseline"], _, _ = cpu_baseline(target_seconds=30.0)
     print(json.dumps(line), flush=True)
     if world > 1:
