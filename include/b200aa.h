@@ -83,8 +83,12 @@ int64_t b200aa_mid_windows(int64_t n_frames, int step_ratio);                  /
 /* ------------------------------------------------------------------ plan --------------- */
 int  b200aa_plan_create(b200aa_plan **out, int fs, int window, int step);
 void b200aa_plan_destroy(b200aa_plan *plan);
-/* 0 = generic mixed-radix kernel, 1 = register-tiled kernel specialised for this window */
+/* kernel that feature launches of this plan use: 0 = generic mixed-radix kernel (any window), 1 = register-tiled
+ * CTA kernel (windows 320/400/480/600/640/800/882), 2 = warp-autonomous pair kernel (windows 32*R: 320/480/640/800/960) */
 int  b200aa_plan_kernel_kind(const b200aa_plan *plan);
+/* restrict the plan to one kernel (testing / A-B runs): -1 = automatic (default), 0, 1 or 2 as above; a kind that
+ * does not exist for the plan's window falls through to the next one */
+int  b200aa_plan_prefer_kernel(b200aa_plan *plan, int kind);
 /* force the generic kernel (testing): returns the previous setting */
 int  b200aa_plan_force_generic(b200aa_plan *plan, int on);
 
@@ -162,6 +166,9 @@ int b200aa_host_free(void *h_ptr);
 int b200aa_peer_buffer_create(size_t bytes, void **d_out, unsigned char *handle_out /* [64] */);
 int b200aa_peer_buffer_open(const unsigned char *handle /* [64] */, void **d_out);
 int b200aa_peer_buffer_close(void *d_ptr, int owner /* 1: the creating rank (frees), 0: a mapping rank (unmaps) */);
+
+/* debugging: when set (device pointer, float32 [n_clips, t_stride, K]) the pair kernel also dumps its |X| rows */
+int b200aa_debug_set_dump(float *d_rows);
 
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t b200aa_launch_count(void);

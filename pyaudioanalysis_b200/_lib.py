@@ -36,6 +36,8 @@ SIGNATURES = {
     "b200aa_plan_destroy": (None, [c_vp]),
     "b200aa_plan_kernel_kind": (c_int, [c_vp]),
     "b200aa_plan_force_generic": (c_int, [c_vp, c_int]),
+    "b200aa_plan_prefer_kernel": (c_int, [c_vp, c_int]),
+    "b200aa_debug_set_dump": (c_int, [c_vp]),
     "b200aa_clip_stats": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "b200aa_st_features": (c_int, [c_vp, c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_vp]),
     "b200aa_spectrogram": (c_int, [c_vp, c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
@@ -106,6 +108,11 @@ class Plan:
 
     def force_generic(self, on=True):
         return lib().b200aa_plan_force_generic(self.handle, 1 if on else 0)
+
+    def prefer_kernel(self, kind):
+        """-1 automatic, 0 generic, 1 register-tiled CTA kernel, 2 warp-autonomous pair kernel (testing / A-B)."""
+        check(lib().b200aa_plan_prefer_kernel(self.handle, int(kind)))
+        return self
 
     def __del__(self):
         try:

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "generic_kernel.cuh"
 #include "fast_kernel.cuh"
+#include "pair_kernel.cuh"
 #include "tables.inl"
 
 using namespace b200aa;
@@ -141,6 +142,10 @@ struct b200aa_plan {
     void *ws[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t ws_cap[4] = {0, 0, 0, 0};
     FastTables fast{};                  // extra device tables of the specialised kernel
+    PairTables pair{};                  // inter-pass twiddles of the warp-autonomous pair kernel (windows 32 * R)
+    int prefer = -1;                    // -1 = automatic, 0 / 1 / 2 = generic / register-tiled / pair kernel only (testing, A/B)
+    unsigned int *d_counters = nullptr; // ring of work counters of the pair kernel (one per in-flight launch)
+    std::atomic<unsigned int> next_counter{0};
     static constexpr int kPipe = 3;     // streams of the chunked host pipeline, each with its own clips / records / features buffers
     cudaStream_t pipe_stream[kPipe] = {nullptr, nullptr, nullptr};
     void *pipe_ws[kPipe][3] = {};
@@ -154,6 +159,8 @@ struct b200aa_plan {
             for (void *w : pipe_ws[k]) if (w) cudaFree(w);
         }
         fast.release();
+        pair.release();
+        if (d_counters) cudaFree(d_counters);
     }
 };
 
@@ -285,14 +292,32 @@ extern "C" int b200aa_plan_create(b200aa_plan **out, int fs, int window, int ste
     if (rc != B200AA_OK) return rc;
     rc = fast_plan_init(fs, window, step, pl->h_blob, pl->bl, &pl->fast, &pl->fast_kind);
     if (rc != B200AA_OK) return rc;
+    rc = pair_plan_init(window, &pl->pair);
+    if (rc != B200AA_OK) return cuda_fail(cudaGetLastError(), "pair_plan_init");
+    CK(cudaMalloc(&pl->d_counters, kCounterRing * sizeof(unsigned int)));
     *out = pl.release();
     return B200AA_OK;
 }
 
 extern "C" void b200aa_plan_destroy(b200aa_plan *plan) { delete plan; }
+static bool use_pair(const b200aa_plan *pl) { return pl->pair.R && !pl->force_generic && (pl->prefer < 0 || pl->prefer == 2); }
+static bool use_fast(const b200aa_plan *pl) { return pl->fast_kind && !pl->force_generic && (pl->prefer < 0 || pl->prefer == 1); }
 extern "C" int b200aa_plan_kernel_kind(const b200aa_plan *plan)
 {
-    return (plan && plan->fast_kind && !plan->force_generic) ? 1 : 0;
+    if (!plan) return 0;
+    return use_pair(plan) ? 2 : (use_fast(plan) ? 1 : 0);
+}
+extern "C" int b200aa_plan_prefer_kernel(b200aa_plan *plan, int kind)
+{
+    if (!plan || kind < -1 || kind > 2) return B200AA_ERR_INVALID;
+    plan->prefer = kind;
+    return B200AA_OK;
+}
+static float *g_pair_dump = nullptr;
+extern "C" int b200aa_debug_set_dump(float *d_rows)
+{
+    g_pair_dump = d_rows;
+    return B200AA_OK;
 }
 extern "C" int b200aa_plan_force_generic(b200aa_plan *plan, int on)
 {
@@ -641,7 +666,13 @@ extern "C" int b200aa_st_features(const b200aa_plan *plan, const void *d_sig, in
     fill_common(p, pl, t, d_sig, dtype, n_clips, n_samples, clip_stride, d_len, d_norm, d_out);
     p.t_stride = t_stride; p.deltas = deltas ? 1 : 0; p.n_out = deltas ? 68 : 34; p.mode = kModeFeatures;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (pl->fast_kind && !pl->force_generic) {
+    if (use_pair(pl)) {
+        unsigned int *ctr = pl->d_counters + (pl->next_counter.fetch_add(1u, std::memory_order_relaxed) % kCounterRing);
+        rc = pair_launch_features(pl->pair, p, pl->sm_count, T, ctr, g_pair_dump, st);
+        if (rc == B200AA_OK) { g_launches.fetch_add(1, std::memory_order_relaxed); return rc; }
+        if (rc != B200AA_ERR_UNSUPPORTED) return rc == B200AA_ERR_CUDA ? cuda_fail(cudaGetLastError(), "pair kernel") : rc;
+    }
+    if (use_fast(pl)) {
         rc = fast_launch_features(pl->fast_kind, pl->fast, p, pl->sm_count, T, st);
         if (rc == B200AA_OK) { g_launches.fetch_add(1, std::memory_order_relaxed); return rc; }
         if (rc != B200AA_ERR_UNSUPPORTED) return rc == B200AA_ERR_CUDA ? cuda_fail(cudaGetLastError(), "fast kernel") : rc;
@@ -670,7 +701,7 @@ extern "C" int b200aa_spectrogram(const b200aa_plan *plan, const void *d_sig, in
     p.mode = kModeSpectrogram;
     p.origin = w; p.row0 = 0; p.rows_total = R; p.rows_launch = R;
     p.rows_valid = std::min<int64_t>(R, b200aa_host::range_len(w, n_samples - w + 1, s));   // :415
-    if (pl->fast_kind && !pl->force_generic) {
+    if (pl->fast_kind && !pl->force_generic && pl->prefer != 0) {
         rc = fast_launch_rows(pl->fast_kind, kModeSpectrogram, pl->fast, p, pl->sm_count, static_cast<cudaStream_t>(stream));
         if (rc == B200AA_OK) { g_launches.fetch_add(1, std::memory_order_relaxed); return rc; }
         if (rc != B200AA_ERR_UNSUPPORTED) return rc == B200AA_ERR_CUDA ? cuda_fail(cudaGetLastError(), "fast kernel") : rc;
@@ -705,7 +736,7 @@ extern "C" int b200aa_chromagram(const b200aa_plan *plan, const void *d_sig, int
     p.mode = kModeChromagram;
     p.origin = w; p.row0 = 0; p.rows_total = R; p.rows_launch = R; p.rows_valid = n_full;
     rc = B200AA_ERR_UNSUPPORTED;
-    if (pl->fast_kind && !pl->force_generic) {
+    if (pl->fast_kind && !pl->force_generic && pl->prefer != 0) {
         rc = fast_launch_rows(pl->fast_kind, kModeChromagram, pl->fast, p, pl->sm_count, st);
         if (rc == B200AA_OK) g_launches.fetch_add(1, std::memory_order_relaxed);
         else if (rc != B200AA_ERR_UNSUPPORTED) return rc == B200AA_ERR_CUDA ? cuda_fail(cudaGetLastError(), "fast kernel") : rc;

@@ -71,10 +71,17 @@ __host__ __device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return ma
 __host__ __device__ __forceinline__ float2 f2fma(float c, float2 a, float2 acc) { return make_float2(fmaf(c, a.x, acc.x), fmaf(c, a.y, acc.y)); }
 #endif
 
+template <int RA, int RB> __host__ __device__ __forceinline__ void fft_pfa(float2 (&v)[RA * RB]);
+template <int RA, int RB> __host__ __device__ __forceinline__ void fft_ct(float2 (&v)[RA * RB]);
+
 template <int P>
 __host__ __device__ __forceinline__ void dft_small(float2 (&x)[P])
 {
-    if constexpr (P == 2) {
+    if constexpr (P == 6) {
+        fft_pfa<2, 3>(x);                                   // composite factors of the longer codelets (30 = 5 x 6)
+    } else if constexpr (P == 8) {
+        fft_ct<2, 4>(x);                                    // 32 = 4 x 8
+    } else if constexpr (P == 2) {
         const float2 a = x[0], b = x[1];
         x[0] = f2add(a, b); x[1] = f2sub(a, b);
     } else if constexpr (P == 4) {
@@ -191,11 +198,14 @@ template <> struct RFactors<15> { static constexpr int A = 3, B = 5; };
 template <> struct RFactors<20> { static constexpr int A = 4, B = 5; };
 template <> struct RFactors<21> { static constexpr int A = 3, B = 7; };
 template <> struct RFactors<16> { static constexpr int A = 4, B = 4; };   // not coprime: Cooley-Tukey
+template <> struct RFactors<25> { static constexpr int A = 5, B = 5; };   // Cooley-Tukey
+template <> struct RFactors<32> { static constexpr int A = 4, B = 8; };   // Cooley-Tukey (8 = 2 x 4)
+template <> struct RFactors<30> { static constexpr int A = 5, B = 6; };   // prime-factor (6 = 2 x 3)
 
 template <int R>
 __host__ __device__ __forceinline__ void fft_r(float2 (&v)[R])
 {
-    if constexpr (R == 16) fft_ct<4, 4>(v);                                   // factors not coprime: Cooley-Tukey
+    if constexpr (R == 16 || R == 25 || R == 32) fft_ct<RFactors<R>::A, RFactors<R>::B>(v);   // factors not coprime: Cooley-Tukey
     else fft_pfa<RFactors<R>::A, RFactors<R>::B>(v);                          // prime-factor (twiddle-free)
 }
 

@@ -1,0 +1,636 @@
+// Warp-autonomous short-term kernel for windows N = 32 * R (R = 10, 15, 20, 25, 30: 320 / 480 / 640 / 800 / 960 samples).
+//
+// One WARP owns a run of consecutive frames of one clip and processes them two at a time with no CTA-wide barrier:
+//   * frames a = 2q and b = 2q + 1 ride through ONE complex FFT of length N: z[n] = sa (xa[n] - xa[0]) + i sb (xb[n] - xb[0])
+//     (sa, sb: per-frame powers of two that bring both frames to unit level, so the float32 error of either spectrum is
+//     relative to its OWN level).  n = 32 n1 + n2, k = k1 + R k2:  lane n2 runs the R-point transform over n1 in
+//     registers (samples come straight from global memory, 2-byte coalesced loads), twiddles by W_N^(n2 k1), one
+//     transpose through shared memory, lane k1 runs the 32-point transform over n2.  Z lands in shared memory in natural
+//     order and |Xa[k]| = |Z[k] + conj Z[N-k]| / 2 sa,  |Xb[k]| = |Z[k] - conj Z[N-k]| / 2 sb  come out with lane = k mod 32
+//     -- no post-twiddle, no packed-real butterfly.
+//   * time-domain rows (zcr / energy / energy entropy) are accumulated per 32-sample row straight from the loaded
+//     registers: sign masks by warp ballot, block energies by one multi-value butterfly reduction; with hop = N / 2 every
+//     sample is visited once (the second halves of a and b are new, the rest is carried in a small ring).
+//   * the spectral rows reuse the half-warp dense pass of fast_kernel.cuh (two frames per warp), the mel / chroma / DCT
+//     contractions are shared-memory dot products over the two |X| rows; feature rows collect in an [8 x 34] tile per warp
+//     and leave as 32-byte row segments.
+// Work items (clip, run of pairs) are handed out by one atomic per item, long runs first and short runs last, and every
+// run starts one pair early (flux and the deltas need frame t - 1), so results do not depend on how a clip was cut.
+#pragma once
+#include "common.cuh"
+#include "dft_codelets.cuh"
+#include "fast_kernel.cuh"
+
+namespace b200aa {
+
+constexpr int kPairWarps = 8;        // warps per CTA (each one autonomous)
+constexpr int kPairMinBlocks = 2;    // 2 x 8 warps per SM at <= 128 registers
+
+template <int R>
+struct PairShape {
+    static constexpr int N = 32 * R, K = N / 2, Kp = DenseShape<K>::Kp, C = Kp / 32;
+    static constexpr int JK = (K + 31) / 32;         // strided rows that hold real bins (k = lane + 32 j)
+    static constexpr int LS = 33;                    // row stride of the transposed pass-1 outputs (float2; odd: conflict-free)
+    static constexpr int TZ = (R * LS > N + 2) ? R * LS : N + 2;   // float2 elements of the transform buffer
+    static constexpr int Lt = N / 10;                // energy-entropy block length (ShortTermFeatures.py:41)
+    static constexpr bool kShareable = (N % 160) == 0;    // half a frame = 5 whole blocks, rows split at lane 0 / 16 only
+    static_assert(2 * TZ >= Kp, "the |X| row of frame a fits the transform buffer");
+    static_assert(Lt >= 32, "a 32-sample row touches two blocks at most");
+};
+
+template <int R>
+struct alignas(16) PairWarpMem {
+    using S = PairShape<R>;
+    float2 tz[S::TZ];                       // pass-1 outputs [k1][LS]  ->  Z[k] (natural order, Z[N] = Z[0])  ->  |X| row of frame a
+    alignas(16) float rowb[2][S::Kp];       // |X| rows of frame b: this step's and the previous step's (alternating)
+    float fv[9 * kFvStride];                // feature rows: row 0 = the frame before the tile, rows 1..8 = the tile
+    float ms[2 * B200AA_N_MEL];             // log-mel energies of a, b
+    float chr[2 * 12];                      // raw chroma sums
+    float parts[2 * 32];                    // spectral-entropy parts of the dense pass
+    float blk[24];                          // block energies: a -> [0, 10), b -> [5, 15) (shared halves) or [10, 20); rests at 20, 21
+};
+
+template <int R>
+struct alignas(16) PairCtaMem {
+    float2 tw[R * 32];                      // W_N^(k1 n2), [k1][n2]
+    alignas(16) int dlane[16 * 4];          // per-lane constants of the dense pass
+    PairWarpMem<R> w[kPairWarps];
+};
+
+struct PairParams {
+    StParams st;
+    const float2 *tw;          // [R][32] inter-pass twiddles
+    unsigned int *counter;     // work counter (zeroed in-stream before the launch)
+    // pairs [0, P) of a clip are cut into n_big runs of seg_big pairs followed by runs of seg_small pairs;
+    // item = run * n_clips + clip, so every clip's long runs are handed out before anybody's short ones
+    int seg_big, n_big, seg_small, segs_per_clip;
+    float *dbg;                // optional dump of the |X| rows [clip][frame][K] (debugging)
+};
+
+template <int R>
+inline size_t pair_smem_bytes(int blob_words) { return sizeof(PairCtaMem<R>) + sizeof(int) * size_t((blob_words + 3) & ~3); }
+
+// ----------------------------------------------------------------------------------------------
+// Sum NV per-lane values over the warp with a halving butterfly: after the call v[0] of lane l holds the
+// total of value number (l >> (5 - log2 P0)), P0 = the power of two >= NV (32, 16 or 8): NV + NV/2 + ... shuffles
+// instead of 5 NV.
+// ----------------------------------------------------------------------------------------------
+template <int P, int NV, int D, int NA>
+__device__ __forceinline__ void mr_halve(float (&v)[NA], int lane)
+{
+    if constexpr (P > 1) {
+        constexpr int H = P / 2;
+        const bool up = lane & D;
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            if (i < NV) {
+                if (i + H < NV) {
+                    const float keep = up ? v[i + H] : v[i], send = up ? v[i] : v[i + H];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, D);
+                } else {
+                    v[i] += __shfl_xor_sync(0xffffffffu, v[i], D);
+                }
+            }
+        }
+        mr_halve<H, (NV < H ? NV : H), D / 2, NA>(v, lane);
+    } else {
+#pragma unroll
+        for (int d = D; d >= 1; d >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], d);
+    }
+}
+template <int NV>
+struct MultiReduce {
+    static constexpr int P0 = NV > 16 ? 32 : (NV > 8 ? 16 : 8);
+    static constexpr int SH = NV > 16 ? 0 : (NV > 8 ? 1 : 2);       // value j ends up in lanes (l >> SH) == j
+    __device__ static __forceinline__ void run(float (&v)[NV], int lane) { mr_halve<P0, NV, 16, NV>(v, lane); }
+};
+
+// ----------------------------------------------------------------------------------------------
+// time-domain accumulation over the 32-sample rows of one frame (u[r] of lane l = sample 32 r + l, as the exact float
+// M0 + x): per-lane sums of y^2 per energy-entropy block, and the number of sign flips from the ballot masks
+//   FULL: all rows, blocks 0..9 (+ the samples beyond 10 blocks);  !FULL: the second half only (blocks 5..9)
+// ----------------------------------------------------------------------------------------------
+template <int R, bool FULL>
+struct TdShape {
+    using S = PairShape<R>;
+    static constexpr int NREST = (S::N % 10) ? 1 : 0;
+    static constexpr int NE = FULL ? 10 + NREST : 5;          // accumulators
+    static constexpr int EB = FULL ? 0 : 5;                   // first block
+    static constexpr int NFIRST = FULL ? 0 : S::N / 2;        // first sample covered
+    static constexpr int ROW0 = NFIRST / 32, LANE0 = NFIRST % 32;
+    static constexpr int ZROW0 = (!FULL && LANE0 == 0) ? ROW0 - 1 : ROW0;     // first row whose sign mask is needed
+    static_assert(FULL || S::kShareable, "half-frame sharing needs whole blocks per half");
+};
+
+template <int R, bool FULL, bool TWO>
+__device__ __forceinline__ void td_frame(const float (&u)[R], float cm, const b200aa_clip_norm &nm, int lane,
+                                         float *e /* [NE] */, int &flips, int &link)
+{
+    using S = PairShape<R>;
+    using Td = TdShape<R, FULL>;
+    constexpr int N = S::N, Lt = S::Lt;
+    unsigned prevP = 0u, prevQ = 0u;
+    int fl = 0, lk = 0;
+#pragma unroll
+    for (int r = Td::ZROW0; r < R; ++r) {
+        const float d = u[r] - cm;
+        // ---- sign masks: P = samples above the clip mean, Q = below (complementary unless a sample can equal the mean)
+        const unsigned P = __ballot_sync(0xffffffffu, d > nm.lo);
+        unsigned Q = 0u;
+        if (TWO) Q = __ballot_sync(0xffffffffu, d < nm.hi);
+        if (FULL && r == 0) { prevP = (P & 1u) << 31; prevQ = (Q & 1u) << 31; }      // sample 0 has no predecessor
+        if (r >= Td::ROW0) {
+            const int n0 = 32 * r;
+            // pairs (n - 1, n) counted for n >= max(1, NFIRST)
+            const int nstart = FULL ? 1 : Td::NFIRST;
+            const unsigned valid = n0 >= nstart ? 0xffffffffu : (n0 + 32 <= nstart ? 0u : (0xffffffffu << (nstart - n0)));
+            const unsigned cP = (P ^ __funnelshift_l(prevP, P, 1)) & valid;
+            fl += __popc(cP);
+            if (!FULL && r == Td::ROW0) lk += int((cP >> Td::LANE0) & 1u);
+            if (TWO) {
+                const unsigned cQ = (Q ^ __funnelshift_l(prevQ, Q, 1)) & valid;
+                fl += __popc(cQ);
+                if (!FULL && r == Td::ROW0) lk += int((cQ >> Td::LANE0) & 1u);
+            }
+            // ---- energy of the normalised samples into the row's block(s)
+            const float y = fmaf(nm.a, d, nm.bp);
+            float q = y * y;
+            if (r == Td::ROW0 && Td::LANE0 > 0) q = lane >= Td::LANE0 ? q : 0.f;
+            const int b0 = (n0 / Lt) < 10 ? (n0 / Lt) : 10;
+            const int end = b0 < 10 ? (b0 + 1) * Lt : N;
+            const int thr = end - n0;                     // samples of this row that still belong to block b0
+            const int i0 = b0 - Td::EB, i1 = (b0 + 1 < 10 ? b0 + 1 : 10) - Td::EB;
+            if (thr >= 32) {
+                if (i0 >= 0 && i0 < Td::NE) e[i0] += q;
+            } else {
+                const bool first = lane < thr;
+                if (i0 >= 0 && i0 < Td::NE) e[i0] += first ? q : 0.f;
+                if (i1 >= 0 && i1 < Td::NE) e[i1] += first ? 0.f : q;
+            }
+        }
+        prevP = P; prevQ = Q;
+    }
+    // one-sided counting saw every change once; |s_n - s_(n-1)| is 2 for a sign change without a zero in between
+    flips = TWO ? fl : 2 * fl;
+    link = TWO ? lk : 2 * lk;
+}
+
+// power of two s with s * rms(x - x0) ~ 1 (E = sum y^2 of the frame, y = a (x - mean)); its inverse
+__device__ __forceinline__ void frame_scale(float E, float inv_a2n, float &s, float &inv_s)
+{
+    const float t = E * inv_a2n;                                // mean square in sample units (>= 0)
+    const int ex = (__float_as_int(t) >> 23) & 0xff;            // biased exponent
+    int k = (127 - ex) >> 1;
+    k = k < -30 ? -30 : (k > 40 ? 40 : k);
+    s = __int_as_float((127 + k) << 23);
+    inv_s = __int_as_float((127 - k) << 23);
+}
+
+// ----------------------------------------------------------------------------------------------
+// kernel
+// ----------------------------------------------------------------------------------------------
+template <int R, bool SHARED>
+__global__ void __launch_bounds__(32 * kPairWarps, kPairMinBlocks) st_pair_kernel(const PairParams pp)
+{
+    using S = PairShape<R>;
+    constexpr int N = S::N, K = S::K, Kp = S::Kp, C = S::C, JK = S::JK, LS = S::LS;
+    static_assert(!SHARED || S::kShareable, "shared halves need N % 160 == 0");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PairCtaMem<R> &cm_ = *reinterpret_cast<PairCtaMem<R> *>(smem_raw);
+    int *const blob_s = reinterpret_cast<int *>(smem_raw + sizeof(PairCtaMem<R>));
+    const StParams &p = pp.st;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < p.bl.words; i += 32 * kPairWarps) blob_s[i] = p.blob[i];
+    for (int i = tid; i < R * 32; i += 32 * kPairWarps) cm_.tw[i] = pp.tw[i];
+    if (tid < 16) {
+        const DenseLane d0_ = dense_lane_init_h<K>(tid);
+        cm_.dlane[tid * 4 + 0] = d0_.split; cm_.dlane[tid * 4 + 1] = d0_.ps; cm_.dlane[tid * 4 + 2] = d0_.pe; cm_.dlane[tid * 4 + 3] = 0;
+    }
+    __syncthreads();
+    const SmallTables tb = bind_tables(blob_s, p.bl);
+    const int *const grp_tab = blob_s + p.bl.mel_grp;
+    PairWarpMem<R> &wm = cm_.w[warp];
+    float *const rowa = reinterpret_cast<float *>(wm.tz);
+    const int step = p.step;
+    const int half = lane >> 4, l16 = lane & 15;
+    const unsigned FULLM = 0xffffffffu;
+
+    for (;;) {
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(pp.counter, 1u);
+        item = __shfl_sync(FULLM, item, 0);
+        if (int64_t(item) >= p.n_items) break;
+        const int seg = int(item / unsigned(p.n_clips));
+        const int64_t b = item - unsigned(seg) * unsigned(p.n_clips);
+        const int64_t len = p.len ? p.len[b] : p.n_samples;
+        const int T = int(len < N ? 0 : (len - N) / step + 1);
+        const int NP = (T + 1) >> 1;                               // pairs of this clip
+        int q0, q1;
+        if (seg < pp.n_big) { q0 = seg * pp.seg_big; q1 = q0 + pp.seg_big; }
+        else { q0 = pp.n_big * pp.seg_big + (seg - pp.n_big) * pp.seg_small; q1 = q0 + pp.seg_small; }
+        if (q0 >= NP) continue;
+        q1 = q1 < NP ? q1 : NP;
+        const b200aa_clip_norm nm = p.norm[b];
+        const bool is16 = p.dtype == B200AA_DTYPE_I16;
+        const char *clip = reinterpret_cast<const char *>(p.sig) + size_t(b) * p.clip_stride * (is16 ? 2 : 4);
+        const float M0 = is16 ? 8421376.f : 0.f;                   // u = M0 + x exactly (2^23 + 2^15 trick for int16)
+        const float cmv = M0 + nm.m;                                // u - cmv = x - m
+        const bool two_sided = !(nm.hi > nm.lo);                    // a sample may equal the clip mean: count both masks
+        const float inv_a2n = 1.f / (nm.a * nm.a * float(N));
+        const float fscale = nm.a * (0.5f / float(K));
+
+        bool fresh = true;          // no state carried from a previous pair (first step of the item)
+        int cur = 0;                // rowb[cur] receives this step's frame b; rowb[cur ^ 1] holds the previous one
+        int tile_n = 0, tile_t0 = 2 * q0;
+        int zprev = 0;              // sign flips inside the first half of frame a (= second half of the previous b)
+        for (int q = q0 - (q0 > 0 ? 1 : 0); q < q1; ++q) {
+            const bool store = q >= q0;
+            const int ta = 2 * q;
+            const bool bvalid = ta + 1 < T;
+            const int tbb = bvalid ? ta + 1 : ta;                  // an odd tail pairs the last frame with itself
+            // ---- samples: lane l holds samples 32 r + l of both frames, as exact floats M0 + x
+            float ua[R], ub[R];
+            if (is16) {
+                const unsigned short *pa = reinterpret_cast<const unsigned short *>(clip) + size_t(ta) * step + lane;
+                const unsigned short *pb = reinterpret_cast<const unsigned short *>(clip) + size_t(tbb) * step + lane;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    ua[r] = __int_as_float(0x4B000000 | (int(__ldg(pa + 32 * r)) ^ 0x8000));
+                    ub[r] = __int_as_float(0x4B000000 | (int(__ldg(pb + 32 * r)) ^ 0x8000));
+                }
+            } else {
+                const float *pa = reinterpret_cast<const float *>(clip) + size_t(ta) * step + lane;
+                const float *pb = reinterpret_cast<const float *>(clip) + size_t(tbb) * step + lane;
+#pragma unroll
+                for (int r = 0; r < R; ++r) { ua[r] = __ldg(pa + 32 * r); ub[r] = __ldg(pb + 32 * r); }
+            }
+            const float u0a = __shfl_sync(FULLM, ua[0], 0), u0b = __shfl_sync(FULLM, ub[0], 0);   // first samples
+            const int ra = store ? 1 + tile_n : 8, rb = store ? 2 + tile_n : 0;     // feature rows (a halo's b is "previous")
+            float *const fva = wm.fv + ra * kFvStride, *const fvb = wm.fv + rb * kFvStride;
+
+            // ---- time-domain rows
+            const bool a_full = !SHARED || fresh;
+            int fl_a, fl_b;
+            {
+                constexpr int NEF = TdShape<R, true>::NE, NREST = TdShape<R, true>::NREST;
+                if constexpr (SHARED) { if (!a_full) {
+                    // steady state: the second halves of a and b are new
+                    float ev[10];
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) ev[i] = 0.f;
+                    int fa_, la_, fb_, lb_;
+                    if (two_sided) { td_frame<R, false, true>(ua, cmv, nm, lane, ev, fa_, la_); td_frame<R, false, true>(ub, cmv, nm, lane, ev + 5, fb_, lb_); }
+                    else { td_frame<R, false, false>(ua, cmv, nm, lane, ev, fa_, la_); td_frame<R, false, false>(ub, cmv, nm, lane, ev + 5, fb_, lb_); }
+                    if (lane < 5) wm.blk[lane] = wm.blk[10 + lane];                 // previous b's second half = a's first half
+                    MultiReduce<10>::run(ev, lane);
+                    __syncwarp();
+                    if ((lane & 1) == 0 && (lane >> 1) < 10) wm.blk[5 + (lane >> 1)] = ev[0];
+                    fl_a = zprev + fa_;                       // first half (carried) + link + second half
+                    fl_b = (fa_ - la_) + fb_;
+                    zprev = fb_ - lb_;
+                } else {
+                    // first step of a run: all of a, the second half of b
+                    float ev[NEF + 5];
+#pragma unroll
+                    for (int i = 0; i < NEF + 5; ++i) ev[i] = 0.f;
+                    int fa_, la_, fb_, lb_;
+                    if (two_sided) { td_frame<R, true, true>(ua, cmv, nm, lane, ev, fa_, la_); td_frame<R, false, true>(ub, cmv, nm, lane, ev + NEF, fb_, lb_); }
+                    else { td_frame<R, true, false>(ua, cmv, nm, lane, ev, fa_, la_); td_frame<R, false, false>(ub, cmv, nm, lane, ev + NEF, fb_, lb_); }
+                    // flips of a's second half alone: b's first half; recount from the shared-half helper
+                    int fh_, lh_;
+                    { float dump[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                      if (two_sided) td_frame<R, false, true>(ua, cmv, nm, lane, dump, fh_, lh_); else td_frame<R, false, false>(ua, cmv, nm, lane, dump, fh_, lh_); }
+                    MultiReduce<NEF + 5>::run(ev, lane);
+                    __syncwarp();
+                    {
+                        constexpr int SH = MultiReduce<NEF + 5>::SH;
+                        const int j = lane >> SH;
+                        if ((lane & ((1 << SH) - 1)) == 0 && j < NEF + 5) wm.blk[j] = ev[0];       // a -> 0..9, b's new half -> 10..14
+                    }
+                    fl_a = fa_;
+                    fl_b = (fh_ - lh_) + fb_;
+                    zprev = fb_ - lb_;
+                } } else {
+                    // independent frames (any hop)
+                    float ev[2 * NEF];
+#pragma unroll
+                    for (int i = 0; i < 2 * NEF; ++i) ev[i] = 0.f;
+                    int la_, lb_;
+                    if (two_sided) { td_frame<R, true, true>(ua, cmv, nm, lane, ev, fl_a, la_); td_frame<R, true, true>(ub, cmv, nm, lane, ev + NEF, fl_b, lb_); }
+                    else { td_frame<R, true, false>(ua, cmv, nm, lane, ev, fl_a, la_); td_frame<R, true, false>(ub, cmv, nm, lane, ev + NEF, fl_b, lb_); }
+                    MultiReduce<2 * NEF>::run(ev, lane);
+                    __syncwarp();
+                    {
+                        constexpr int SH = MultiReduce<2 * NEF>::SH;
+                        const int j = lane >> SH;
+                        if ((lane & ((1 << SH) - 1)) == 0 && j < 2 * NEF) {
+                            const int f = j >= NEF ? 1 : 0, i = j - f * NEF;
+                            wm.blk[i < 10 ? 10 * f + i : 20 + f] = ev[0];
+                        }
+                    }
+                    (void)NREST;
+                }
+            }
+            __syncwarp();
+            float Ea, Eb;           // frame energies sum y^2 (warp-uniform)
+            {
+                constexpr int OB = SHARED ? 5 : 10;
+                const bool own = l16 < 10;
+                const float e = own ? wm.blk[half * OB + l16] : 0.f;
+                float tot = half_sum(e);
+                if (!SHARED && TdShape<R, true>::NREST) tot += wm.blk[20 + half];
+                const float sj = fdiv(e, tot + B200AA_EPS);
+                const float H = half_sum(own ? -sj * flog2(sj + B200AA_EPS) : 0.f);
+                if (l16 == 0) {
+                    float *fv = half ? fvb : fva;
+                    fv[0] = float(half ? fl_b : fl_a) * 0.5f / float(N - 1);
+                    fv[1] = tot / float(N);
+                    fv[2] = H;
+                }
+                Ea = __shfl_sync(FULLM, tot, 0);
+                Eb = __shfl_sync(FULLM, tot, 16);
+            }
+
+            // ---- pack the two frames into one complex sequence and transform: pass 1 (lane = n2, R points over n1)
+            float sa, isa, sb, isb;
+            frame_scale(Ea, inv_a2n, sa, isa);
+            frame_scale(Eb, inv_a2n, sb, isb);
+            bool a_flat, b_flat;        // every sample equals the frame's first one: the spectrum is exactly zero beyond DC
+            {
+                float2 z[R];
+                const float oa = -u0a * sa, ob = -u0b * sb;
+                float2 zz = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    z[r] = make_float2(fmaf(ua[r], sa, oa), fmaf(ub[r], sb, ob));
+                    zz = __ffma2_rn(z[r], z[r], zz);
+                }
+                // A constant frame must come out as exact zeros (the reference's float64 spectrum is ~1e-17 there, and
+                // log10(. + eps) makes that visible): its partner would otherwise leak ~1e-7 of its own level into it
+                a_flat = !__any_sync(FULLM, zz.x > 0.f);
+                b_flat = !__any_sync(FULLM, zz.y > 0.f);
+                fft_r<R>(z);
+                wm.tz[lane] = z[0];
+#pragma unroll
+                for (int k1 = 1; k1 < R; ++k1) wm.tz[k1 * LS + lane] = cmul(z[k1], cm_.tw[k1 * 32 + lane]);
+            }
+            __syncwarp();
+            // ---- pass 2 (lane = k1, 32 points over n2) -> Z[k1 + R k2] in natural order
+            {
+                float2 v[32];
+                const int row = lane < R ? lane : 0;
+#pragma unroll
+                for (int n2 = 0; n2 < 32; ++n2) v[n2] = wm.tz[row * LS + n2];
+                fft_r<32>(v);
+                __syncwarp();
+                if (lane < R) {
+#pragma unroll
+                    for (int k2 = 0; k2 < 32; ++k2) wm.tz[lane + R * k2] = v[k2];
+                    if (lane == 0) wm.tz[N] = v[0];
+                }
+            }
+            __syncwarp();
+            // ---- separate the two spectra: bins k = lane + 32 j
+            float xa[C], xb[C];
+            {
+                const float fa = a_flat ? 0.f : fscale * isa, fb = b_flat ? 0.f : fscale * isb;
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
+                    const int k = lane + 32 * j;
+                    xa[j] = 0.f; xb[j] = 0.f;
+                    if (j < JK && k < K) {
+                        const float2 zk = wm.tz[k], pk = wm.tz[N - k];
+                        const float sx_ = zk.x + pk.x, sy_ = zk.y - pk.y, dx_ = zk.x - pk.x, dy_ = zk.y + pk.y;
+                        xa[j] = fsqrt_pos(fmaf(sx_, sx_, sy_ * sy_)) * fa;
+                        xb[j] = fsqrt_pos(fmaf(dx_, dx_, dy_ * dy_)) * fb;
+                    }
+                }
+                if (lane == 0) {
+                    // DC: a sum(x - x0) + N (a (x0 - m) + bp), over K
+                    const float2 z0 = wm.tz[0];
+                    xa[0] = fabsf(fmaf(nm.a * isa, z0.x, float(N) * fmaf(nm.a, u0a - cmv, nm.bp))) / float(K);
+                    xb[0] = fabsf(fmaf(nm.a * isb, z0.y, float(N) * fmaf(nm.a, u0b - cmv, nm.bp))) / float(K);
+                }
+            }
+            __syncwarp();                    // every lane has read Z: the buffer becomes the |X| row of frame a
+            float *const rowbn = wm.rowb[cur];
+#pragma unroll
+            for (int j = 0; j < C; ++j) { rowa[lane + 32 * j] = xa[j]; rowbn[lane + 32 * j] = xb[j]; }
+            if (pp.dbg) {
+#pragma unroll
+                for (int j = 0; j < JK; ++j) {
+                    const int k = lane + 32 * j;
+                    if (k < K) {
+                        pp.dbg[(size_t(b) * p.t_stride + ta) * K + k] = xa[j];
+                        if (bvalid) pp.dbg[(size_t(b) * p.t_stride + ta + 1) * K + k] = xb[j];
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- spectral rows: half-warp per frame (dense pass of fast_kernel.cuh)
+            {
+                const float *X = half ? rowbn : rowa;
+                const float *Xp = half ? rowa : (fresh ? rowa : wm.rowb[cur ^ 1]);
+                const float rs = row_sum_h<K>(Xp, l16);
+                spectral_features_h<K>(X, Xp, rs, cm_.dlane + l16 * 4, wm.parts + half * 32, half ? fvb : fva, l16, true, nullptr);
+            }
+            // ---- mel filters + log10 (16 lanes per frame, <= 3 filters each), raw chroma sums (12 lanes per frame)
+            {
+                const float *X = half ? rowbn : rowa;
+#pragma unroll
+                for (int h = 0; h < 3; ++h) {
+                    const int i = grp_tab[3 * l16 + h];
+                    if (i >= 0) {
+                        const int s0 = tb.mel_start[i], cnt = tb.mel_count[i], off = tb.mel_off[i];
+                        float acc = 0.f;
+#pragma unroll 4
+                        for (int t = 0; t < cnt; ++t) acc = fmaf(X[s0 + t], tb.mel_w[off + t], acc);
+                        wm.ms[half * B200AA_N_MEL + i] = 0.30102999566398120f * flog2(acc + B200AA_EPS);   // log10
+                    }
+                }
+                if (l16 < 12) {
+                    const int e0 = tb.chr_off[l16], e1 = tb.chr_off[l16 + 1];
+                    float acc = 0.f;
+                    for (int e = e0; e < e1; ++e) {
+                        const float v = X[tb.chr_bin[e]];
+                        acc = fmaf(v * v, tb.chr_w[e], acc);
+                    }
+                    wm.chr[half * 12 + l16] = acc;
+                }
+            }
+            __syncwarp();
+            // ---- folded DCT-II (see flat_dct in fast_kernel.cuh): 52 (frame, row, half) slots over two rounds
+#pragma unroll
+            for (int base = 0; base < 64; base += 32) {
+                const int t = base + lane;
+                const int f = t / 26, r = t - f * 26;
+                const int c = r >> 1, h = r & 1;
+                const bool act = t < 52;
+                float acc = 0.f;
+                if (act) {
+                    const float *m = wm.ms + f * B200AA_N_MEL;
+                    const float kap = m[0];
+                    const float *row = tb.dct + c * 41;
+                    const float sgn = (c & 1) ? -1.f : 1.f;
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) {
+                        const int n = 10 * h + j;
+                        acc = fmaf(row[n], fmaf(sgn, m[39 - n] - kap, m[n] - kap), acc);
+                    }
+                }
+                acc += __shfl_xor_sync(FULLM, acc, 1);
+                if (act && h == 0) {
+                    if (c == 0) acc = fmaf(6.324555320336759f, wm.ms[f * B200AA_N_MEL], acc);      // sqrt(1/40) * 40 * k
+                    (f ? fvb : fva)[8 + c] = acc;
+                }
+            }
+            chroma_finalize_h(wm.chr + half * 12, half ? fvb : fva, l16, true);
+            __syncwarp();
+
+            // ---- tile bookkeeping / store
+            if (store) {
+                tile_n += bvalid ? 2 : 1;
+                if (tile_n == 8 || q == q1 - 1) {
+                    float *const out_b = p.out + size_t(b) * p.n_out * p.t_stride + tile_t0;
+                    for (int e = lane; e < p.n_out * 8; e += 32) {
+                        const int f = e >> 3, c = e & 7;
+                        if (c >= tile_n) continue;
+                        float val;
+                        if (f < B200AA_N_BASE) val = wm.fv[(1 + c) * kFvStride + f];
+                        else {
+                            const int fb_ = f - B200AA_N_BASE;
+                            val = (tile_t0 + c == 0) ? 0.f : wm.fv[(1 + c) * kFvStride + fb_] - wm.fv[c * kFvStride + fb_];
+                        }
+                        out_b[size_t(f) * p.t_stride + c] = val;
+                    }
+                    __syncwarp();
+                    wm.fv[lane] = wm.fv[tile_n * kFvStride + lane];
+                    if (lane < 2) wm.fv[32 + lane] = wm.fv[tile_n * kFvStride + 32 + lane];
+                    tile_t0 += tile_n;
+                    tile_n = 0;
+                    __syncwarp();
+                }
+            }
+            fresh = false;
+            cur ^= 1;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+inline int pair_r_for_window(int window)
+{
+    switch (window) {
+    case 320: return 10;
+    case 480: return 15;
+    case 640: return 20;
+    case 800: return 25;
+    case 960: return 30;
+    default: return 0;
+    }
+}
+
+struct PairTables {
+    float2 *d_tw = nullptr;
+    int R = 0;
+    void release() { if (d_tw) cudaFree(d_tw); d_tw = nullptr; }
+};
+
+inline int pair_plan_init(int window, PairTables *pt)
+{
+    const int R = pair_r_for_window(window);
+    pt->R = 0;
+    if (!R) return B200AA_OK;
+    if (getenv("B200AA_NO_PAIR")) return B200AA_OK;
+    const int N = 32 * R;
+    const double pi = 3.14159265358979323846264338327950288;
+    std::vector<float2> tw(size_t(R) * 32);
+    for (int k1 = 0; k1 < R; ++k1)
+        for (int n2 = 0; n2 < 32; ++n2) {
+            const double a = -2.0 * pi * double((k1 * n2) % N) / double(N);
+            tw[size_t(k1) * 32 + n2] = make_float2(float(std::cos(a)), float(std::sin(a)));
+        }
+    if (cudaMalloc(&pt->d_tw, tw.size() * sizeof(float2)) != cudaSuccess) return B200AA_ERR_CUDA;
+    if (cudaMemcpy(pt->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) return B200AA_ERR_CUDA;
+    pt->R = R;
+    return B200AA_OK;
+}
+
+#ifndef B200AA_LAYOUT_ONLY
+template <int R, bool SHARED>
+inline int pair_launch_t(const PairTables &pt, const StParams &p, int sm_count, int64_t T, unsigned int *counter, float *dbg,
+                         cudaStream_t st)
+{
+    const size_t smem = pair_smem_bytes<R>(p.bl.words);
+    if (smem > 113u * 1024u) return B200AA_ERR_UNSUPPORTED;
+    auto kern = st_pair_kernel<R, SHARED>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200AA_ERR_CUDA;
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * kPairWarps, smem) != cudaSuccess) return B200AA_ERR_CUDA;
+    occ = occ < 1 ? 1 : occ;
+    PairParams pp;
+    pp.st = p;
+    pp.tw = pt.d_tw;
+    pp.counter = counter;
+    pp.dbg = dbg;
+    const int64_t NP = (T + 1) / 2;                                  // pairs per (full-length) clip
+    const int64_t slots = int64_t(sm_count) * occ * kPairWarps;      // resident warps
+    const int64_t total = NP * p.n_clips;
+    int64_t share = (total + slots - 1) / slots;                     // pairs per warp if perfectly balanced
+    if (share < 1) share = 1;
+    // long runs (a third of a warp's share, cheap halo) for the first ~3/4 of every clip, short ones to level the tail
+    int64_t small = share / 10;
+    small = small < 4 ? 4 : (small > 48 ? 48 : small);
+    int64_t big = share / 3;
+    big = big < small ? small : big;
+    if (big > NP) big = NP;
+    if (small > NP) small = NP;
+    if (const char *ov = getenv("B200AA_PAIR_SEG")) {                // tuning override: "big,small"
+        long a = 0, b2 = 0;
+        if (sscanf(ov, "%ld,%ld", &a, &b2) == 2 && a > 0 && b2 > 0) { big = a < NP ? a : NP; small = b2 < NP ? b2 : NP; }
+    }
+    int64_t n_big = (NP * 3 / 4) / big;
+    if (total <= slots * 2) { n_big = 0; }                           // tiny launches: latency wins, short runs only
+    const int64_t left = NP - n_big * big;
+    const int64_t n_small = (left + small - 1) / small;
+    pp.seg_big = int(big); pp.n_big = int(n_big); pp.seg_small = int(small);
+    pp.segs_per_clip = int(n_big + n_small);
+    pp.st.n_items = int64_t(pp.segs_per_clip) * p.n_clips;
+    if (pp.st.n_items >= (int64_t(1) << 31) || T >= (int64_t(1) << 30)) return B200AA_ERR_UNSUPPORTED;
+    int64_t grid = (pp.st.n_items + kPairWarps - 1) / kPairWarps;
+    if (grid > int64_t(sm_count) * occ) grid = int64_t(sm_count) * occ;
+    if (getenv("B200AA_DEBUG"))
+        fprintf(stderr, "[b200aa] pair kernel R=%d shared=%d: smem %zu B, %d CTAs/SM, grid %lld, %lld items (%d x %d + %lld x %d pairs per clip)\n",
+                R, int(SHARED), smem, occ, (long long)grid, (long long)pp.st.n_items, pp.n_big, pp.seg_big, (long long)n_small, pp.seg_small);
+    if (cudaMemsetAsync(counter, 0, sizeof(unsigned int), st) != cudaSuccess) return B200AA_ERR_CUDA;
+    kern<<<(unsigned)grid, 32 * kPairWarps, smem, st>>>(pp);
+    return cudaPeekAtLastError() == cudaSuccess ? B200AA_OK : B200AA_ERR_CUDA;
+}
+
+template <int R>
+inline int pair_launch_r(const PairTables &pt, const StParams &p, int sm_count, int64_t T, unsigned int *counter, float *dbg, cudaStream_t st)
+{
+    constexpr int N = 32 * R;
+    if (PairShape<R>::kShareable && p.step == N / 2) return pair_launch_t<R, PairShape<R>::kShareable>(pt, p, sm_count, T, counter, dbg, st);
+    return pair_launch_t<R, false>(pt, p, sm_count, T, counter, dbg, st);
+}
+
+// feature launch through the pair kernel; B200AA_ERR_UNSUPPORTED = let another kernel take it
+inline int pair_launch_features(const PairTables &pt, const StParams &p, int sm_count, int64_t T, unsigned int *counter, float *dbg,
+                                cudaStream_t st)
+{
+    // 2-byte (int16) / 4-byte (float) loads need nothing beyond natural alignment; frames must fit 32-bit indices
+    switch (pt.R) {
+    case 10: return pair_launch_r<10>(pt, p, sm_count, T, counter, dbg, st);
+    case 15: return pair_launch_r<15>(pt, p, sm_count, T, counter, dbg, st);
+    case 20: return pair_launch_r<20>(pt, p, sm_count, T, counter, dbg, st);
+    case 25: return pair_launch_r<25>(pt, p, sm_count, T, counter, dbg, st);
+    case 30: return pair_launch_r<30>(pt, p, sm_count, T, counter, dbg, st);
+    default: return B200AA_ERR_UNSUPPORTED;
+    }
+}
+#endif  // B200AA_LAYOUT_ONLY
+
+}  // namespace b200aa

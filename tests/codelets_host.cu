@@ -105,8 +105,61 @@ static void check_shape()
     report("shape", R1, R2, err / mag);
 }
 
+// the pair kernel's transform (csrc/pair_kernel.cuh): two real frames of N = 32 * R samples through ONE complex FFT,
+// n = 32 n1 + n2, k = k1 + R k2, |Xa[k]| = |Z[k] + conj Z[N-k]| / 2 sa, |Xb[k]| = |Z[k] - conj Z[N-k]| / 2 sb;
+// "lanes" are loops here, the index maps and codelets are the kernel's
+template <int R>
+static void check_pair()
+{
+    constexpr int N = 32 * R, K = N / 2;
+    unsigned seed = 4242u + R;
+    std::vector<float> xa(N), xb(N);
+    for (int n = 0; n < N; ++n) {
+        xa[n] = float((int(lcg(seed) % 65536) - 32768));          // loud frame
+        xb[n] = float((int(lcg(seed) % 61) - 30) + 7);              // quiet frame (60 dB below) with a DC offset
+    }
+    const float sa = 1.f / 16384.f, sb = 1.f / 16.f;                 // per-frame power-of-two scales
+    std::vector<float2> T(size_t(R) * 33), Z(N + 1);
+    for (int n2 = 0; n2 < 32; ++n2) {                                // pass 1: lane n2
+        float2 z[R];
+        for (int r = 0; r < R; ++r) z[r] = make_float2(sa * (xa[32 * r + n2] - xa[0]), sb * (xb[32 * r + n2] - xb[0]));
+        fft_r<R>(z);
+        for (int k1 = 0; k1 < R; ++k1) {
+            const double a = -2.0 * M_PI * double((k1 * n2) % N) / double(N);
+            T[size_t(k1) * 33 + n2] = k1 == 0 ? z[0] : hmul(z[k1], make_float2(float(std::cos(a)), float(std::sin(a))));
+        }
+    }
+    for (int k1 = 0; k1 < R; ++k1) {                                 // pass 2: lane k1
+        float2 v[32];
+        for (int n2 = 0; n2 < 32; ++n2) v[n2] = T[size_t(k1) * 33 + n2];
+        fft_r<32>(v);
+        for (int k2 = 0; k2 < 32; ++k2) Z[k1 + R * k2] = v[k2];
+    }
+    Z[N] = Z[0];
+    double erra = 0.0, errb = 0.0, rmsa = 0.0, rmsb = 0.0;
+    for (int k = 1; k < K; ++k) {
+        const float2 zk = Z[k], pk = Z[N - k];
+        const double ga = std::hypot(double(zk.x + pk.x), double(zk.y - pk.y)) / (2.0 * sa);
+        const double gb = std::hypot(double(zk.x - pk.x), double(zk.y + pk.y)) / (2.0 * sb);
+        double ar = 0, ai = 0, br = 0, bi = 0;
+        for (int n = 0; n < N; ++n) {
+            const double a = -2.0 * M_PI * double((long(k) * n) % N) / double(N);
+            ar += xa[n] * std::cos(a); ai += xa[n] * std::sin(a);
+            br += xb[n] * std::cos(a); bi += xb[n] * std::sin(a);
+        }
+        const double ra = std::hypot(ar, ai), rb = std::hypot(br, bi);
+        erra = std::fmax(erra, std::fabs(ra - ga)); errb = std::fmax(errb, std::fabs(rb - gb));
+        rmsa += ra * ra; rmsb += rb * rb;
+    }
+    // error of either spectrum relative to its OWN rms level (the quiet frame must not inherit the loud one's error)
+    report("pair", R, 0, erra / std::sqrt(rmsa / K));
+    report("pair", R, 1, errb / std::sqrt(rmsb / K));
+}
+
 int main()
 {
+    check_pair<10>(); check_pair<15>(); check_pair<20>(); check_pair<25>(); check_pair<30>();
+    check_codelet<25>(); check_codelet<30>(); check_codelet<32>();
     check_codelet<10>(); check_codelet<12>(); check_codelet<15>(); check_codelet<16>(); check_codelet<20>(); check_codelet<21>();
     check_shape<20, 20>(); check_shape<21, 21>(); check_shape<20, 10>(); check_shape<20, 12>();
     check_shape<20, 15>(); check_shape<16, 10>(); check_shape<20, 16>();
