@@ -292,8 +292,17 @@ extern "C" int b200aa_plan_create(b200aa_plan **out, int fs, int window, int ste
     if (rc != B200AA_OK) return rc;
     rc = fast_plan_init(fs, window, step, pl->h_blob, pl->bl, &pl->fast, &pl->fast_kind);
     if (rc != B200AA_OK) return rc;
-    rc = pair_plan_init(window, &pl->pair);
-    if (rc != B200AA_OK) return cuda_fail(cudaGetLastError(), "pair_plan_init");
+    if (pair_r_for_window(window) && pl->tables_status == B200AA_OK) {
+        std::vector<double> mel, chr, dct;
+        b200aa_host::build_mel(fs, pl->K, mel);
+        b200aa_host::build_chroma(fs, pl->K, chr);
+        b200aa_host::build_dct(dct);
+        std::vector<int> pblob;
+        PairBlobLayout pbl{};
+        build_pair_blob(mel, chr, dct, pl->K, pblob, pbl);
+        rc = pair_plan_init(window, pblob, pbl, &pl->pair);
+        if (rc != B200AA_OK) return cuda_fail(cudaGetLastError(), "pair_plan_init");
+    }
     CK(cudaMalloc(&pl->d_counters, kCounterRing * sizeof(unsigned int)));
     *out = pl.release();
     return B200AA_OK;

@@ -63,12 +63,16 @@ __host__ __device__ constexpr int cx_modinv(int a, int m)
 // -DB200AA_NO_F32X2 builds use the scalar forms)
 #if !defined(B200AA_NO_F32X2) && defined(__CUDA_ARCH__)
 __device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+// a - b as one FFMA2 (b * -1 + a: the same single rounding); FADD2 has no per-operand negation, the negated copy cost two
+// extra instructions per subtraction (3 % of the pair kernel's instructions, profiles/pair_r2_v1)
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
 __device__ __forceinline__ float2 f2fma(float c, float2 a, float2 acc) { return __ffma2_rn(make_float2(c, c), a, acc); }
+__device__ __forceinline__ float2 f2mulc(float c, float2 a) { return __fmul2_rn(make_float2(c, c), a); }
 #else
 __host__ __device__ __forceinline__ float2 f2add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __host__ __device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __host__ __device__ __forceinline__ float2 f2fma(float c, float2 a, float2 acc) { return make_float2(fmaf(c, a.x, acc.x), fmaf(c, a.y, acc.y)); }
+__host__ __device__ __forceinline__ float2 f2mulc(float c, float2 a) { return make_float2(c * a.x, c * a.y); }
 #endif
 
 template <int RA, int RB> __host__ __device__ __forceinline__ void fft_pfa(float2 (&v)[RA * RB]);
@@ -207,6 +211,74 @@ __host__ __device__ __forceinline__ void fft_r(float2 (&v)[R])
 {
     if constexpr (R == 16 || R == 25 || R == 32) fft_ct<RFactors<R>::A, RFactors<R>::B>(v);   // factors not coprime: Cooley-Tukey
     else fft_pfa<RFactors<R>::A, RFactors<R>::B>(v);                          // prime-factor (twiddle-free)
+}
+
+// ----------------------------------------------------------------------------------------------
+// 32-point forward FFT in "two sequences per register pair" form (pair kernel, pass 2).
+// Input: re[m] = (Re x[2m], Re x[2m+1]), im[m] = (Im x[2m], Im x[2m+1]), m < 16 -- the .x halves are the even-indexed
+// samples, the .y halves the odd-indexed ones.  Both 16-point sub-transforms run in the same FP32x2 instructions
+// (identical twiddles, real constants broadcast to both halves; multiplying by -i is a swap of roles, not an
+// instruction), then X[k] = E[k] + W32^k O[k], X[k+16] = E[k] - W32^k O[k] in scalar FMAs.  ~280 instructions
+// instead of ~440 for the generic (re, im)-packed Cooley-Tukey codelet.
+// ----------------------------------------------------------------------------------------------
+struct Soa2 { float2 re, im; };      // one complex element of each of the two sequences
+
+__host__ __device__ __forceinline__ void soa_dft4(Soa2 &x0, Soa2 &x1, Soa2 &x2, Soa2 &x3)
+{
+    const float2 ar = f2add(x0.re, x2.re), ai = f2add(x0.im, x2.im), br = f2sub(x0.re, x2.re), bi = f2sub(x0.im, x2.im);
+    const float2 cr = f2add(x1.re, x3.re), ci = f2add(x1.im, x3.im), dr = f2sub(x1.re, x3.re), di = f2sub(x1.im, x3.im);
+    x0.re = f2add(ar, cr); x0.im = f2add(ai, ci);
+    x2.re = f2sub(ar, cr); x2.im = f2sub(ai, ci);
+    x1.re = f2add(br, di); x1.im = f2sub(bi, dr);        // b - i d
+    x3.re = f2sub(br, di); x3.im = f2add(bi, dr);        // b + i d
+}
+// x *= W_Q^e = cos(2 pi e / Q) - i sin(2 pi e / Q), compile-time e
+template <int Q, int E>
+__host__ __device__ __forceinline__ void soa_twiddle(Soa2 &x)
+{
+    constexpr int e = E % Q;
+    if constexpr (e == 0) {
+    } else if constexpr (4 * e == Q) {              // -i
+        const float2 t = x.re; x.re = x.im; x.im = make_float2(-t.x, -t.y);
+    } else {
+        constexpr float wr = float(cx_cos_turn(e, Q)), wi = float(-cx_sin_turn(e, Q));
+        const float2 r = f2fma(-wi, x.im, f2mulc(wr, x.re));
+        const float2 i = f2fma(wr, x.im, f2mulc(wi, x.re));
+        x.re = r; x.im = i;
+    }
+}
+__host__ __device__ __forceinline__ void fft32_soa(const float2 (&re)[16], const float2 (&im)[16], float2 (&out)[32])
+{
+    Soa2 t[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) { t[m].re = re[m]; t[m].im = im[m]; }
+    // 16 = 4 x 4, m = 4 a + b, k = ka + 4 kb: four DFT4 over a, twiddle W16^(b ka), four DFT4 over b
+#pragma unroll
+    for (int b = 0; b < 4; ++b) soa_dft4(t[b], t[4 + b], t[8 + b], t[12 + b]);            // t[4 ka + b]
+    soa_twiddle<16, 1>(t[4 + 1]); soa_twiddle<16, 2>(t[8 + 1]); soa_twiddle<16, 3>(t[12 + 1]);
+    soa_twiddle<16, 2>(t[4 + 2]); soa_twiddle<16, 4>(t[8 + 2]); soa_twiddle<16, 6>(t[12 + 2]);
+    soa_twiddle<16, 3>(t[4 + 3]); soa_twiddle<16, 6>(t[8 + 3]); soa_twiddle<16, 9>(t[12 + 3]);
+#pragma unroll
+    for (int ka = 0; ka < 4; ++ka) soa_dft4(t[4 * ka], t[4 * ka + 1], t[4 * ka + 2], t[4 * ka + 3]);   // -> E/O[ka + 4 kb] at t[4 ka + kb]
+    // radix-2 combination of the even (.x) and odd (.y) transforms
+    constexpr Trig<32> T = make_trig<32>();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int ka = k & 3, kb = k >> 2;
+        const Soa2 v = t[4 * ka + kb];
+        const float er = v.re.x, ei = v.im.x, orr = v.re.y, oi = v.im.y;
+        if (k == 0) {
+            out[0] = make_float2(er + orr, ei + oi);
+            out[16] = make_float2(er - orr, ei - oi);
+        } else if (k == 8) {                         // W = -i: t = (oi, -or)
+            out[8] = make_float2(er + oi, ei - orr);
+            out[24] = make_float2(er - oi, ei + orr);
+        } else {
+            const float c = T.c[k], sn = T.s[k];     // W32^k = c - i sn:  t = (or c + oi sn, oi c - or sn)
+            out[k] = make_float2(fmaf(oi, sn, fmaf(orr, c, er)), fmaf(-orr, sn, fmaf(oi, c, ei)));
+            out[k + 16] = make_float2(fmaf(-oi, sn, fmaf(-orr, c, er)), fmaf(orr, sn, fmaf(-oi, c, ei)));
+        }
+    }
 }
 
 }  // namespace b200aa

@@ -19,6 +19,9 @@
 #pragma once
 #include "common.cuh"
 #include "dft_codelets.cuh"
+#include <algorithm>
+#include <cstring>
+#include <utility>
 #include "fast_kernel.cuh"
 
 namespace b200aa {
@@ -30,7 +33,8 @@ template <int R>
 struct PairShape {
     static constexpr int N = 32 * R, K = N / 2, Kp = DenseShape<K>::Kp, C = Kp / 32;
     static constexpr int JK = (K + 31) / 32;         // strided rows that hold real bins (k = lane + 32 j)
-    static constexpr int LS = 33;                    // row stride of the transposed pass-1 outputs (float2; odd: conflict-free)
+    static constexpr int LS = 34;                    // row stride (floats) of the two transposed pass-1 planes (re, im): even, so the
+                                                     // second pass reads (n2, n2 + 1) pairs as aligned 8-byte words, conflict-free per half-warp
     static constexpr int TZ = (R * LS > N + 2) ? R * LS : N + 2;   // float2 elements of the transform buffer
     static constexpr int Lt = N / 10;                // energy-entropy block length (ShortTermFeatures.py:41)
     static constexpr bool kShareable = (N % 160) == 0;    // half a frame = 5 whole blocks, rows split at lane 0 / 16 only
@@ -41,10 +45,12 @@ struct PairShape {
 template <int R>
 struct alignas(16) PairWarpMem {
     using S = PairShape<R>;
-    float2 tz[S::TZ];                       // pass-1 outputs [k1][LS]  ->  Z[k] (natural order, Z[N] = Z[0])  ->  |X| row of frame a
+    float2 tz[S::TZ];                       // pass-1 outputs, planes re[k1][LS] | im[k1][LS]  ->  Z[k] (natural order, Z[N] = Z[0])  ->  |X| row of a
     alignas(16) float rowb[2][S::Kp];       // |X| rows of frame b: this step's and the previous step's (alternating)
     float fv[9 * kFvStride];                // feature rows: row 0 = the frame before the tile, rows 1..8 = the tile
-    float ms[2 * B200AA_N_MEL];             // log-mel energies of a, b
+    float msraw[2 * B200AA_N_MEL];          // mel filter outputs of a, b
+    float ms[2 * B200AA_N_MEL];             // log10 of them
+    float mfold[2 * B200AA_N_MEL];          // folded halves for the DCT: [f][0..19] sums, [f][20..39] differences
     float chr[2 * 12];                      // raw chroma sums
     float parts[2 * 32];                    // spectral-entropy parts of the dense pass
     float blk[24];                          // block energies: a -> [0, 10), b -> [5, 15) (shared halves) or [10, 20); rests at 20, 21
@@ -57,8 +63,20 @@ struct alignas(16) PairCtaMem {
     PairWarpMem<R> w[kPairWarps];
 };
 
+// constant tables of the pair kernel (int32 words, copied to shared memory once per CTA)
+struct PairBlobLayout {
+    int dct;        // [13 x 41] DCT rows (float)
+    int mel_rec;    // [LQ][16] one record per (step q, lane): first bin | filter << 16 | flush << 24
+    int mel_w;      // [LQ][16] float4: the four tap weights of the record (16-byte aligned)
+    int chr;        // [CT][16] {bin, weight}: tap t of pitch class l (lanes 12..15: padding)
+    int lq, ct;     // steps per lane
+    int words;
+};
+
 struct PairParams {
     StParams st;
+    const int *pblob;          // tables above
+    PairBlobLayout pbl;
     const float2 *tw;          // [R][32] inter-pass twiddles
     unsigned int *counter;     // work counter (zeroed in-stream before the launch)
     // pairs [0, P) of a clip are cut into n_big runs of seg_big pairs followed by runs of seg_small pairs;
@@ -69,6 +87,123 @@ struct PairParams {
 
 template <int R>
 inline size_t pair_smem_bytes(int blob_words) { return sizeof(PairCtaMem<R>) + sizeof(int) * size_t((blob_words + 3) & ~3); }
+
+__device__ __forceinline__ float fsqrt_fast(float x)        // MUFU.SQRT (2 ulp, 0 -> 0)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Dense spectral rows of two frames per warp (half-warp each): spectral_features_h of fast_kernel.cuh with the previous
+// frame's row sum taken from where it already exists -- half 1 (frame b) receives half 0's (frame a's) sum by shuffle,
+// half 0 the carried sum of the previous pair's b -- instead of re-reading the previous row.
+// ----------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void pair_spectral(const float *X, const float *Xp, float sxp_carried, bool own_prev, const int *dlp,
+                                              float *parts, float *fv, int l, int half)
+{
+    constexpr int C2 = HalfShape<K>::C2, CB = HalfShape<K>::CB;
+    const int k0 = l * CB;
+    const int4 dlv = *reinterpret_cast<const int4 *>(dlp);        // {split (pairs), ps, pe, -}
+    const float2 *X2 = reinterpret_cast<const float2 *>(X) + l * C2;
+    const float2 *Xp2 = reinterpret_cast<const float2 *>(Xp) + l * C2;
+    float2 x2[C2];
+#pragma unroll
+    for (int j = 0; j < C2; ++j) x2[j] = X2[j];
+    float sx = 0.f, s1 = 0.f, sb = 0.f;
+    float2 plo2 = make_float2(0.f, 0.f), phi2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < C2; ++j) {
+        const float t = x2[j].x + x2[j].y;
+        sx += t;
+        s1 = fmaf(float(2 * j + 1), t, s1);
+        sb += x2[j].y;
+        const float2 sq = __fmul2_rn(x2[j], x2[j]);
+        if (j < dlv.x) plo2 = f2add(plo2, sq); else phi2 = f2add(phi2, sq);
+    }
+    const float plo = plo2.x + plo2.y, phi = phi2.x + phi2.y, part = plo + phi;
+    float sk = fmaf(float(k0), sx, s1 + sb);         // sum (k0 + i + 1) x_i
+    parts[2 * l] = plo;
+    parts[2 * l + 1] = phi;
+    {   // two sums in 4 exchanges
+        const bool up = l & 8;
+        float keep = up ? sk : sx;
+        const float give = up ? sx : sk;
+        keep += __shfl_xor_sync(0xffffffffu, give, 8);
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+        sx = __shfl_sync(0xffffffffu, keep, 0, 16);
+        sk = __shfl_sync(0xffffffffu, keep, 8, 16);
+    }
+    // previous frame's row sum: frame b <- frame a (the other half, just computed), frame a <- carried (or itself)
+    const float sx_a = __shfl_sync(0xffffffffu, sx, 0);
+    const float sxp = half ? sx_a : (own_prev ? sx : sxp_carried);
+    float incl = part;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const float n = __shfl_up_sync(0xffffffffu, incl, o, 16);
+        if (l >= o) incl += n;
+    }
+    const float sxx = __shfl_sync(0xffffffffu, incl, 15, 16);
+    constexpr float invK = 1.f / float(K);
+    const float cen = sx > 0.f ? fdiv(sk, sx) * invK : 0.f;
+    const float nx = fdiv(1.f, sx + float(K) * B200AA_EPS);
+    const float np_ = fdiv(1.f, sxp + float(K) * B200AA_EPS);
+    const float thr = 0.90f * sxx - B200AA_EPS;
+    float2 d2 = make_float2(float(k0 + 1) * invK - cen, float(k0 + 2) * invK - cen);
+    const float2 dstep = make_float2(2.f * invK, 2.f * invK);
+    const float2 nx2 = make_float2(nx, nx), mnp2 = make_float2(-np_, -np_);
+    float2 sp2 = make_float2(0.f, 0.f), fl2 = make_float2(0.f, 0.f);
+    float run = incl - part, below = 0.f;
+#pragma unroll
+    for (int j = 0; j < C2; ++j) {
+        sp2 = __ffma2_rn(__fmul2_rn(d2, d2), x2[j], sp2);
+        d2 = f2add(d2, dstep);
+        const float2 df = __ffma2_rn(x2[j], nx2, __fmul2_rn(Xp2[j], mnp2));
+        fl2 = __ffma2_rn(df, df, fl2);
+        run = fmaf(x2[j].x, x2[j].x, run);
+        below += run > thr ? 0.f : 1.f;
+        run = fmaf(x2[j].y, x2[j].y, run);
+        below += run > thr ? 0.f : 1.f;
+    }
+    const float sp = sp2.x + sp2.y, fl = fl2.x + fl2.y;
+    __syncwarp();
+    float e = 0.f;
+    constexpr int MAXP = 2 * (HalfShape<K>::Lb / CB + 2);
+#pragma unroll
+    for (int q = 0; q < MAXP; ++q) e += (dlv.y + q < dlv.z) ? parts[dlv.y + q] : 0.f;
+    float ent = 0.f;
+    if (l < 10) {
+        const float sj = fdiv(e, sxx + B200AA_EPS);
+        ent = -sj * flog2(sj + B200AA_EPS);
+    }
+    float q4;
+    {   // four sums in 4 exchanges: lanes 0-3 spread, 4-7 flux, 8-11 rolloff count, 12-15 entropy
+        const bool up8 = l & 8, up4 = l & 4;
+        float k0_ = up8 ? below : sp, k1_ = up8 ? ent : fl;
+        const float g0_ = up8 ? sp : below, g1_ = up8 ? fl : ent;
+        k0_ += __shfl_xor_sync(0xffffffffu, g0_, 8);
+        k1_ += __shfl_xor_sync(0xffffffffu, g1_, 8);
+        float kk = up4 ? k1_ : k0_;
+        const float gg = up4 ? k0_ : k1_;
+        kk += __shfl_xor_sync(0xffffffffu, gg, 4);
+        kk += __shfl_xor_sync(0xffffffffu, kk, 2);
+        kk += __shfl_xor_sync(0xffffffffu, kk, 1);
+        q4 = kk;
+    }
+    if (l == 0) {
+        fv[3] = cen;
+        fv[4] = sx > 0.f ? fsqrt_pos(fdiv(q4, sx)) : 0.f;
+        fv[34] = sx;
+        fv[35] = sxx;
+    }
+    if (l == 4) fv[6] = q4;
+    if (l == 8) fv[7] = q4 >= float(K) ? 0.f : q4 * invK;
+    if (l == 12) fv[5] = q4;
+    __syncwarp();
+}
 
 // ----------------------------------------------------------------------------------------------
 // Sum NV per-lane values over the warp with a halving butterfly: after the call v[0] of lane l holds the
@@ -200,17 +335,21 @@ __global__ void __launch_bounds__(32 * kPairWarps, kPairMinBlocks) st_pair_kerne
     int *const blob_s = reinterpret_cast<int *>(smem_raw + sizeof(PairCtaMem<R>));
     const StParams &p = pp.st;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < p.bl.words; i += 32 * kPairWarps) blob_s[i] = p.blob[i];
+    for (int i = tid; i < pp.pbl.words; i += 32 * kPairWarps) blob_s[i] = pp.pblob[i];
     for (int i = tid; i < R * 32; i += 32 * kPairWarps) cm_.tw[i] = pp.tw[i];
     if (tid < 16) {
         const DenseLane d0_ = dense_lane_init_h<K>(tid);
         cm_.dlane[tid * 4 + 0] = d0_.split; cm_.dlane[tid * 4 + 1] = d0_.ps; cm_.dlane[tid * 4 + 2] = d0_.pe; cm_.dlane[tid * 4 + 3] = 0;
     }
     __syncthreads();
-    const SmallTables tb = bind_tables(blob_s, p.bl);
-    const int *const grp_tab = blob_s + p.bl.mel_grp;
+    const float *const t_dct = reinterpret_cast<const float *>(blob_s + pp.pbl.dct);
+    const int *const t_mrec = blob_s + pp.pbl.mel_rec;
+    const float4 *const t_mw = reinterpret_cast<const float4 *>(blob_s + pp.pbl.mel_w);
+    const int2 *const t_chr = reinterpret_cast<const int2 *>(blob_s + pp.pbl.chr);
+    const int LQ = pp.pbl.lq, CT = pp.pbl.ct;
     PairWarpMem<R> &wm = cm_.w[warp];
     float *const rowa = reinterpret_cast<float *>(wm.tz);
+    float *const t_re = reinterpret_cast<float *>(wm.tz), *const t_im = t_re + R * LS;
     const int step = p.step;
     const int half = lane >> 4, l16 = lane & 15;
     const unsigned FULLM = 0xffffffffu;
@@ -370,18 +509,25 @@ __global__ void __launch_bounds__(32 * kPairWarps, kPairMinBlocks) st_pair_kerne
                 a_flat = !__any_sync(FULLM, zz.x > 0.f);
                 b_flat = !__any_sync(FULLM, zz.y > 0.f);
                 fft_r<R>(z);
-                wm.tz[lane] = z[0];
+                t_re[lane] = z[0].x; t_im[lane] = z[0].y;
 #pragma unroll
-                for (int k1 = 1; k1 < R; ++k1) wm.tz[k1 * LS + lane] = cmul(z[k1], cm_.tw[k1 * 32 + lane]);
+                for (int k1 = 1; k1 < R; ++k1) {
+                    const float2 w = cmul(z[k1], cm_.tw[k1 * 32 + lane]);
+                    t_re[k1 * LS + lane] = w.x; t_im[k1 * LS + lane] = w.y;
+                }
             }
             __syncwarp();
-            // ---- pass 2 (lane = k1, 32 points over n2) -> Z[k1 + R k2] in natural order
+            // ---- pass 2 (lane = k1, 32 points over n2, even / odd n2 side by side in FP32x2) -> Z[k1 + R k2] in natural order
             {
                 float2 v[32];
-                const int row = lane < R ? lane : 0;
+                {
+                    float2 re[16], im[16];
+                    const int row = lane < R ? lane : 0;
+                    const float2 *pr = reinterpret_cast<const float2 *>(t_re + row * LS), *pi = reinterpret_cast<const float2 *>(t_im + row * LS);
 #pragma unroll
-                for (int n2 = 0; n2 < 32; ++n2) v[n2] = wm.tz[row * LS + n2];
-                fft_r<32>(v);
+                    for (int m = 0; m < 16; ++m) { re[m] = pr[m]; im[m] = pi[m]; }
+                    fft32_soa(re, im, v);
+                }
                 __syncwarp();
                 if (lane < R) {
 #pragma unroll
@@ -401,8 +547,8 @@ __global__ void __launch_bounds__(32 * kPairWarps, kPairMinBlocks) st_pair_kerne
                     if (j < JK && k < K) {
                         const float2 zk = wm.tz[k], pk = wm.tz[N - k];
                         const float sx_ = zk.x + pk.x, sy_ = zk.y - pk.y, dx_ = zk.x - pk.x, dy_ = zk.y + pk.y;
-                        xa[j] = fsqrt_pos(fmaf(sx_, sx_, sy_ * sy_)) * fa;
-                        xb[j] = fsqrt_pos(fmaf(dx_, dx_, dy_ * dy_)) * fb;
+                        xa[j] = fsqrt_fast(fmaf(sx_, sx_, sy_ * sy_)) * fa;
+                        xb[j] = fsqrt_fast(fmaf(dx_, dx_, dy_ * dy_)) * fb;
                     }
                 }
                 if (lane == 0) {
@@ -427,62 +573,59 @@ __global__ void __launch_bounds__(32 * kPairWarps, kPairMinBlocks) st_pair_kerne
                 }
             }
             __syncwarp();
-            // ---- spectral rows: half-warp per frame (dense pass of fast_kernel.cuh)
+            // ---- spectral rows: half-warp per frame
             {
                 const float *X = half ? rowbn : rowa;
                 const float *Xp = half ? rowa : (fresh ? rowa : wm.rowb[cur ^ 1]);
-                const float rs = row_sum_h<K>(Xp, l16);
-                spectral_features_h<K>(X, Xp, rs, cm_.dlane + l16 * 4, wm.parts + half * 32, half ? fvb : fva, l16, true, nullptr);
+                const float carried = wm.fv[(ra - 1) * kFvStride + 34];          // row sum of the previous pair's b (unused when fresh)
+                pair_spectral<K>(X, Xp, carried, fresh, cm_.dlane + l16 * 4, wm.parts + half * 32, half ? fvb : fva, l16, half);
             }
-            // ---- mel filters + log10 (16 lanes per frame, <= 3 filters each), raw chroma sums (12 lanes per frame)
+            // ---- mel filters: 16 lanes per frame, LQ steps of four taps each (whole filters per lane, balanced on the host);
+            //      raw chroma sums: 12 lanes per frame, CT taps each
             {
                 const float *X = half ? rowbn : rowa;
-#pragma unroll
-                for (int h = 0; h < 3; ++h) {
-                    const int i = grp_tab[3 * l16 + h];
-                    if (i >= 0) {
-                        const int s0 = tb.mel_start[i], cnt = tb.mel_count[i], off = tb.mel_off[i];
-                        float acc = 0.f;
-#pragma unroll 4
-                        for (int t = 0; t < cnt; ++t) acc = fmaf(X[s0 + t], tb.mel_w[off + t], acc);
-                        wm.ms[half * B200AA_N_MEL + i] = 0.30102999566398120f * flog2(acc + B200AA_EPS);   // log10
-                    }
+                float acc = 0.f;
+                for (int q = 0; q < LQ; ++q) {
+                    const int rec = t_mrec[q * 16 + l16];
+                    const float4 w = t_mw[q * 16 + l16];
+                    const float *xp = X + (rec & 0xffff);
+                    acc = fmaf(xp[0], w.x, acc);
+                    acc = fmaf(xp[1], w.y, acc);
+                    acc = fmaf(xp[2], w.z, acc);
+                    acc = fmaf(xp[3], w.w, acc);
+                    if (rec & (1 << 24)) { wm.msraw[half * B200AA_N_MEL + ((rec >> 16) & 0xff)] = acc; acc = 0.f; }
                 }
-                if (l16 < 12) {
-                    const int e0 = tb.chr_off[l16], e1 = tb.chr_off[l16 + 1];
-                    float acc = 0.f;
-                    for (int e = e0; e < e1; ++e) {
-                        const float v = X[tb.chr_bin[e]];
-                        acc = fmaf(v * v, tb.chr_w[e], acc);
-                    }
-                    wm.chr[half * 12 + l16] = acc;
+                float ch = 0.f;
+                for (int t = 0; t < CT; ++t) {
+                    const int2 e = t_chr[t * 16 + l16];
+                    const float v = X[e.x];
+                    ch = fmaf(v * v, __int_as_float(e.y), ch);
                 }
+                if (l16 < 12) wm.chr[half * 12 + l16] = ch;
             }
             __syncwarp();
-            // ---- folded DCT-II (see flat_dct in fast_kernel.cuh): 52 (frame, row, half) slots over two rounds
+            // ---- log10, fold (m_n - k) +- (m_(39-n) - k) with k = m_0 (see flat_dct in fast_kernel.cuh), 13 x 20 DCT rows
 #pragma unroll
-            for (int base = 0; base < 64; base += 32) {
-                const int t = base + lane;
-                const int f = t / 26, r = t - f * 26;
-                const int c = r >> 1, h = r & 1;
-                const bool act = t < 52;
+            for (int t = lane; t < 2 * B200AA_N_MEL; t += 32) wm.ms[t] = 0.30102999566398120f * flog2(wm.msraw[t] + B200AA_EPS);
+            __syncwarp();
+#pragma unroll
+            for (int t = lane; t < 2 * B200AA_N_MEL; t += 32) {
+                const int f = t >= B200AA_N_MEL ? 1 : 0, r = t - f * B200AA_N_MEL;
+                const int kind = r >= 20 ? 1 : 0, n = r - 20 * kind;
+                const float *m = wm.ms + f * B200AA_N_MEL;
+                const float a = m[n], bq = m[39 - n], kap = m[0];
+                wm.mfold[t] = kind ? a - bq : (a - kap) + (bq - kap);
+            }
+            __syncwarp();
+            {
+                const int c = l16 < B200AA_N_MFCC ? l16 : 0;
+                const float *src = wm.mfold + half * B200AA_N_MEL + 20 * (c & 1);
+                const float *row = t_dct + c * 41;
                 float acc = 0.f;
-                if (act) {
-                    const float *m = wm.ms + f * B200AA_N_MEL;
-                    const float kap = m[0];
-                    const float *row = tb.dct + c * 41;
-                    const float sgn = (c & 1) ? -1.f : 1.f;
 #pragma unroll
-                    for (int j = 0; j < 10; ++j) {
-                        const int n = 10 * h + j;
-                        acc = fmaf(row[n], fmaf(sgn, m[39 - n] - kap, m[n] - kap), acc);
-                    }
-                }
-                acc += __shfl_xor_sync(FULLM, acc, 1);
-                if (act && h == 0) {
-                    if (c == 0) acc = fmaf(6.324555320336759f, wm.ms[f * B200AA_N_MEL], acc);      // sqrt(1/40) * 40 * k
-                    (f ? fvb : fva)[8 + c] = acc;
-                }
+                for (int n = 0; n < 20; ++n) acc = fmaf(row[n], src[n], acc);
+                if (c == 0) acc = fmaf(6.324555320336759f, wm.ms[half * B200AA_N_MEL], acc);      // sqrt(1/40) * 40 * k
+                if (l16 < B200AA_N_MFCC) (half ? fvb : fva)[8 + c] = acc;
             }
             chroma_finalize_h(wm.chr + half * 12, half ? fvb : fva, l16, true);
             __syncwarp();
@@ -491,21 +634,25 @@ __global__ void __launch_bounds__(32 * kPairWarps, kPairMinBlocks) st_pair_kerne
             if (store) {
                 tile_n += bvalid ? 2 : 1;
                 if (tile_n == 8 || q == q1 - 1) {
-                    float *const out_b = p.out + size_t(b) * p.n_out * p.t_stride + tile_t0;
-                    for (int e = lane; e < p.n_out * 8; e += 32) {
-                        const int f = e >> 3, c = e & 7;
-                        if (c >= tile_n) continue;
-                        float val;
-                        if (f < B200AA_N_BASE) val = wm.fv[(1 + c) * kFvStride + f];
-                        else {
-                            const int fb_ = f - B200AA_N_BASE;
-                            val = (tile_t0 + c == 0) ? 0.f : wm.fv[(1 + c) * kFvStride + fb_] - wm.fv[c * kFvStride + fb_];
+                    // lane -> (feature row f0 + 4 i, frame c): eight consecutive lanes write 32 consecutive bytes of one output row
+                    const int c = lane & 7, f0 = lane >> 3;
+                    if (c < tile_n) {
+                        float *const out_b = p.out + size_t(b) * p.n_out * p.t_stride + tile_t0 + c;
+                        const float *cur_row = wm.fv + (1 + c) * kFvStride, *prv_row = wm.fv + c * kFvStride;
+                        const bool first = tile_t0 + c == 0;              // frame 0 of the clip: deltas are zero
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) {
+                            const int f = f0 + 4 * i;
+                            if (f < B200AA_N_BASE) {
+                                const float v = cur_row[f];
+                                out_b[size_t(f) * p.t_stride] = v;
+                                if (p.n_out > B200AA_N_BASE) out_b[size_t(f + B200AA_N_BASE) * p.t_stride] = first ? 0.f : v - prv_row[f];
+                            }
                         }
-                        out_b[size_t(f) * p.t_stride + c] = val;
                     }
                     __syncwarp();
                     wm.fv[lane] = wm.fv[tile_n * kFvStride + lane];
-                    if (lane < 2) wm.fv[32 + lane] = wm.fv[tile_n * kFvStride + 32 + lane];
+                    if (lane < 4) wm.fv[32 + lane] = wm.fv[tile_n * kFvStride + 32 + lane];     // incl. the row sum (slot 34)
                     tile_t0 += tile_n;
                     tile_n = 0;
                     __syncwarp();
@@ -534,11 +681,97 @@ inline int pair_r_for_window(int window)
 
 struct PairTables {
     float2 *d_tw = nullptr;
+    int *d_pblob = nullptr;
+    PairBlobLayout pbl{};
     int R = 0;
-    void release() { if (d_tw) cudaFree(d_tw); d_tw = nullptr; }
+    void release()
+    {
+        if (d_tw) cudaFree(d_tw);
+        if (d_pblob) cudaFree(d_pblob);
+        d_tw = nullptr; d_pblob = nullptr;
+    }
 };
 
-inline int pair_plan_init(int window, PairTables *pt)
+// Pair-kernel tables from the dense host tables (mel [40 x K], chroma [12 x K], dct [13 x 40], all float64):
+//   mel: every filter is cut into groups of four consecutive taps (zero padded); whole filters are dealt to 16 lanes
+//        (longest first, to the least loaded lane) and every lane walks its list in LQ steps, flushing a filter's sum
+//        at the filter's last group;   chroma: per pitch class a list of (bin, weight) taps padded to CT entries.
+inline void build_pair_blob(const std::vector<double> &mel, const std::vector<double> &chr, const std::vector<double> &dct, int K,
+                            std::vector<int> &blob, PairBlobLayout &bl)
+{
+    struct Quad { int start, fid, last; float w[4]; };
+    std::vector<std::vector<Quad>> per_filter(B200AA_N_MEL);
+    for (int i = 0; i < B200AA_N_MEL; ++i) {
+        int lo = -1, hi = -1;
+        if (!mel.empty())
+            for (int k = 0; k < K; ++k)
+                if (mel[size_t(i) * K + k] != 0.0) { if (lo < 0) lo = k; hi = k; }
+        if (lo < 0) { lo = 0; hi = -1; }                       // empty filter: one all-zero group (its log is log10(eps))
+        const int nq = hi >= lo ? (hi - lo + 4) / 4 : 1;
+        for (int q = 0; q < nq; ++q) {
+            Quad qd{};
+            const int s = lo + 4 * q;
+            int s2 = s;
+            if (s2 + 4 > K) s2 = K - 4 > 0 ? K - 4 : 0;        // keep the four reads inside the row
+            qd.start = s2; qd.fid = i; qd.last = q == nq - 1;
+            for (int j = 0; j < 4; ++j) {
+                const int k = s2 + j;
+                qd.w[j] = (k >= s && k < s + 4 && k <= hi && k < K) ? float(mel[size_t(i) * K + k]) : 0.f;
+            }
+            per_filter[i].push_back(qd);
+        }
+    }
+    std::vector<int> order(B200AA_N_MEL);
+    for (int i = 0; i < B200AA_N_MEL; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return per_filter[a].size() > per_filter[b].size(); });
+    std::vector<std::vector<Quad>> lanes(16);
+    for (int i : order) {
+        int best = 0;
+        for (int l = 1; l < 16; ++l) if (lanes[l].size() < lanes[best].size()) best = l;
+        lanes[best].insert(lanes[best].end(), per_filter[i].begin(), per_filter[i].end());
+    }
+    size_t lq = 1;
+    for (auto &l : lanes) lq = l.size() > lq ? l.size() : lq;
+    // chroma taps
+    std::vector<std::vector<std::pair<int, float>>> taps(12);
+    size_t ct = 1;
+    if (!chr.empty())
+        for (int c = 0; c < 12; ++c) {
+            for (int k = 0; k < K; ++k)
+                if (chr[size_t(c) * K + k] != 0.0) taps[c].push_back({k, float(chr[size_t(c) * K + k])});
+            ct = taps[c].size() > ct ? taps[c].size() : ct;
+        }
+    auto fbits = [](float f) { int w; std::memcpy(&w, &f, 4); return w; };
+    blob.clear();
+    bl.dct = 0;
+    blob.resize(13 * 41 + 3, 0);
+    for (int r = 0; r < 13; ++r)
+        for (int n = 0; n < 40; ++n) blob[r * 41 + n] = fbits(float(dct[size_t(r) * 40 + n]));
+    while (blob.size() % 4) blob.push_back(0);
+    bl.mel_rec = (int)blob.size();
+    for (size_t q = 0; q < lq; ++q)
+        for (int l = 0; l < 16; ++l) {
+            int rec = 0;                                        // padding step: bin 0, zero weights, no flush
+            if (q < lanes[l].size()) rec = lanes[l][q].start | (lanes[l][q].fid << 16) | (lanes[l][q].last << 24);
+            blob.push_back(rec);
+        }
+    bl.mel_w = (int)blob.size();                                // multiple of 4 words: 16-byte aligned
+    for (size_t q = 0; q < lq; ++q)
+        for (int l = 0; l < 16; ++l)
+            for (int j = 0; j < 4; ++j) blob.push_back(q < lanes[l].size() ? fbits(lanes[l][q].w[j]) : 0);
+    bl.chr = (int)blob.size();                                  // 8-byte aligned
+    for (size_t t = 0; t < ct; ++t)
+        for (int l = 0; l < 16; ++l) {
+            const bool have = l < 12 && t < taps[l].size();
+            blob.push_back(have ? taps[l][t].first : 0);
+            blob.push_back(have ? fbits(taps[l][t].second) : 0);
+        }
+    while (blob.size() % 4) blob.push_back(0);
+    bl.lq = (int)lq; bl.ct = (int)ct;
+    bl.words = (int)blob.size();
+}
+
+inline int pair_plan_init(int window, const std::vector<int> &h_pblob, const PairBlobLayout &pbl, PairTables *pt)
 {
     const int R = pair_r_for_window(window);
     pt->R = 0;
@@ -554,6 +787,9 @@ inline int pair_plan_init(int window, PairTables *pt)
         }
     if (cudaMalloc(&pt->d_tw, tw.size() * sizeof(float2)) != cudaSuccess) return B200AA_ERR_CUDA;
     if (cudaMemcpy(pt->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) return B200AA_ERR_CUDA;
+    if (cudaMalloc(&pt->d_pblob, h_pblob.size() * sizeof(int)) != cudaSuccess) return B200AA_ERR_CUDA;
+    if (cudaMemcpy(pt->d_pblob, h_pblob.data(), h_pblob.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return B200AA_ERR_CUDA;
+    pt->pbl = pbl;
     pt->R = R;
     return B200AA_OK;
 }
@@ -563,7 +799,7 @@ template <int R, bool SHARED>
 inline int pair_launch_t(const PairTables &pt, const StParams &p, int sm_count, int64_t T, unsigned int *counter, float *dbg,
                          cudaStream_t st)
 {
-    const size_t smem = pair_smem_bytes<R>(p.bl.words);
+    const size_t smem = pair_smem_bytes<R>(pt.pbl.words);
     if (smem > 113u * 1024u) return B200AA_ERR_UNSUPPORTED;
     auto kern = st_pair_kernel<R, SHARED>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200AA_ERR_CUDA;
@@ -573,6 +809,8 @@ inline int pair_launch_t(const PairTables &pt, const StParams &p, int sm_count, 
     PairParams pp;
     pp.st = p;
     pp.tw = pt.d_tw;
+    pp.pblob = pt.d_pblob;
+    pp.pbl = pt.pbl;
     pp.counter = counter;
     pp.dbg = dbg;
     const int64_t NP = (T + 1) / 2;                                  // pairs per (full-length) clip

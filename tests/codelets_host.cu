@@ -105,6 +105,32 @@ static void check_shape()
     report("shape", R1, R2, err / mag);
 }
 
+// the two-sequences-per-register 32-point codelet of the pair kernel's second pass
+static void check_fft32_soa()
+{
+    unsigned seed = 777u;
+    float2 re[16], im[16], out[32];
+    double xr[32], xi[32];
+    for (int n = 0; n < 32; ++n) {
+        const float a = float((double(lcg(seed) % 20001) - 10000.0) / 10000.0), b = float((double(lcg(seed) % 20001) - 10000.0) / 10000.0);
+        xr[n] = a; xi[n] = b;
+        if (n & 1) { re[n / 2].y = a; im[n / 2].y = b; } else { re[n / 2].x = a; im[n / 2].x = b; }
+    }
+    fft32_soa(re, im, out);
+    double err = 0.0, mag = 0.0;
+    for (int k = 0; k < 32; ++k) {
+        double sr = 0.0, si = 0.0;
+        for (int n = 0; n < 32; ++n) {
+            const double a = -2.0 * M_PI * double((k * n) % 32) / 32.0;
+            sr += xr[n] * std::cos(a) - xi[n] * std::sin(a);
+            si += xr[n] * std::sin(a) + xi[n] * std::cos(a);
+        }
+        err = std::fmax(err, std::fmax(std::fabs(sr - out[k].x), std::fabs(si - out[k].y)));
+        mag = std::fmax(mag, std::hypot(sr, si));
+    }
+    report("soa32", 32, 0, err / mag);
+}
+
 // the pair kernel's transform (csrc/pair_kernel.cuh): two real frames of N = 32 * R samples through ONE complex FFT,
 // n = 32 n1 + n2, k = k1 + R k2, |Xa[k]| = |Z[k] + conj Z[N-k]| / 2 sa, |Xb[k]| = |Z[k] - conj Z[N-k]| / 2 sb;
 // "lanes" are loops here, the index maps and codelets are the kernel's
@@ -130,9 +156,12 @@ static void check_pair()
         }
     }
     for (int k1 = 0; k1 < R; ++k1) {                                 // pass 2: lane k1
-        float2 v[32];
-        for (int n2 = 0; n2 < 32; ++n2) v[n2] = T[size_t(k1) * 33 + n2];
-        fft_r<32>(v);
+        float2 re[16], im[16], v[32];
+        for (int m = 0; m < 16; ++m) {
+            re[m] = make_float2(T[size_t(k1) * 33 + 2 * m].x, T[size_t(k1) * 33 + 2 * m + 1].x);
+            im[m] = make_float2(T[size_t(k1) * 33 + 2 * m].y, T[size_t(k1) * 33 + 2 * m + 1].y);
+        }
+        fft32_soa(re, im, v);
         for (int k2 = 0; k2 < 32; ++k2) Z[k1 + R * k2] = v[k2];
     }
     Z[N] = Z[0];
@@ -158,6 +187,7 @@ static void check_pair()
 
 int main()
 {
+    check_fft32_soa();
     check_pair<10>(); check_pair<15>(); check_pair<20>(); check_pair<25>(); check_pair<30>();
     check_codelet<25>(); check_codelet<30>(); check_codelet<32>();
     check_codelet<10>(); check_codelet<12>(); check_codelet<15>(); check_codelet<16>(); check_codelet<20>(); check_codelet<21>();
