@@ -625,7 +625,12 @@ static int launch_generic(const b200aa_plan *pl, StParams &p, int64_t rows_max, 
         smem = generic_smem_bytes(G, p.Nc, p.Kp, p.bl.words);
         if (smem <= (G == 8 ? 100u * 1024u : 226u * 1024u)) break;   // 227 KB is the per-CTA opt-in maximum
     }
-    if (G < 1) return B200AA_ERR_UNSUPPORTED;
+    const bool big = G < 1;            // one frame does not fit shared memory: window-sized arrays go to global memory
+    if (big) {
+        G = 1;
+        smem = generic_smem_bytes(G, p.Nc, p.Kp, p.bl.words, false);
+        if (p.Nc > (1 << 20)) return B200AA_ERR_UNSUPPORTED;          // 2^21-sample windows: beyond any use of the path
+    }
     p.G = G;
     // segments: long enough to amortise the 2-frame halo, short enough to balance the SMs
     int64_t seg = rows_max;
@@ -640,13 +645,28 @@ static int launch_generic(const b200aa_plan *pl, StParams &p, int64_t rows_max, 
     p.seg_len = seg;
     p.segs_per_clip = std::max<int64_t>(1, (rows_max + seg - 1) / seg);
     p.n_items = p.segs_per_clip * p.n_clips;
-    auto kern = st_generic_kernel<MODE>;
+    if (p.n_items == 0) return B200AA_OK;
+    if (big) {
+        auto kern = st_generic_kernel<MODE, true>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t grid = std::min<int64_t>(p.n_items, int64_t(pl->sm_count) * 2);
+        p.scratch_stride = generic_big_bytes(G, p.Nc, p.Kp);
+        void *scratch = nullptr;
+        CK(cudaMallocAsync(&scratch, p.scratch_stride * size_t(grid), st));      // stream-ordered: safe across concurrent launches
+        p.scratch = static_cast<unsigned char *>(scratch);
+        kern<<<(unsigned)grid, kThreads, smem, st>>>(p);
+        const cudaError_t e = cudaGetLastError();
+        cudaFreeAsync(scratch, st);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (e != cudaSuccess) return cuda_fail(e, "st_generic_kernel (large window)");
+        return B200AA_OK;
+    }
+    auto kern = st_generic_kernel<MODE, false>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
     occ = std::max(1, occ);
     const int64_t grid = std::min<int64_t>(p.n_items, int64_t(pl->sm_count) * occ);
-    if (grid == 0) return B200AA_OK;
     kern<<<(unsigned)grid, kThreads, smem, st>>>(p);
     CK_LAUNCH("st_generic_kernel");
     return B200AA_OK;

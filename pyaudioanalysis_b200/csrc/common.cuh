@@ -53,6 +53,10 @@ struct StParams {
     int radix[kMaxRadix];
     int G;                          // frames per group (generic kernel)
     int mode;
+    // large windows (generic kernel, BIG form): the transform ping-pong buffers and the |X| rows of every CTA live in
+    // global memory (stream-ordered allocation per launch) instead of shared memory
+    unsigned char *scratch;
+    size_t scratch_stride;          // bytes per CTA
 };
 
 __device__ __forceinline__ float warp_sum(float v)

@@ -8,11 +8,15 @@
 
 namespace b200aa {
 
-// shared-memory bytes of the generic kernel for G frames per group
-inline size_t generic_smem_bytes(int G, int Nc, int Kp, int blob_words)
+// bytes of the per-CTA arrays that scale with the window: transform ping-pong buffers + magnitude rows (+ previous frame)
+inline size_t generic_big_bytes(int G, int Nc, int Kp)
 {
-    size_t b = size_t(G) * Nc * sizeof(float2) * 2;          // ping-pong transform buffers
-    b += size_t(G + 1) * Kp * sizeof(float);                 // magnitude rows (+ previous frame)
+    return (size_t(G) * Nc * sizeof(float2) * 2 + size_t(G + 1) * Kp * sizeof(float) + 15) & ~size_t(15);
+}
+// shared-memory bytes of the generic kernel for G frames per group (big = false: the window-sized arrays live in global memory)
+inline size_t generic_smem_bytes(int G, int Nc, int Kp, int blob_words, bool big_in_smem = true)
+{
+    size_t b = big_in_smem ? generic_big_bytes(G, Nc, Kp) : 0;
     b += size_t(G + 1) * kFvStride * sizeof(float);          // feature rows (+ previous frame)
     b += size_t(kWarps) * B200AA_N_MEL * sizeof(float);      // mel scratch
     b += size_t(G + 1) * sizeof(float);                      // row sums
@@ -47,15 +51,19 @@ __device__ __forceinline__ void stockham_pass_bfly(const float2 *src, float2 *ds
     }
 }
 
-template <int MODE>
+// BIG: windows whose transform does not fit shared memory (e.g. the 1 s windows of music_thumbnailing at 44.1 kHz,
+// audioSegmentation.py:1137-1139): same code, the window-sized arrays of the CTA sit in global memory (L2 resident),
+// __syncthreads() orders the passes as before.
+template <int MODE, bool BIG = false>
 __global__ void __launch_bounds__(kThreads, 2) st_generic_kernel(const StParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int G = p.G, Nc = p.Nc, K = p.K, Kp = p.Kp, w = p.window, fn = p.fft_n;
-    float2 *bufA = reinterpret_cast<float2 *>(smem_raw);
+    unsigned char *const big = BIG ? p.scratch + size_t(blockIdx.x) * p.scratch_stride : smem_raw;
+    float2 *bufA = reinterpret_cast<float2 *>(big);
     float2 *bufB = bufA + size_t(G) * Nc;
     float *Xrows = reinterpret_cast<float *>(bufB + size_t(G) * Nc);    // row 0 = previous frame
-    float *fvrows = Xrows + size_t(G + 1) * Kp;                          // row 0 = previous frame
+    float *fvrows = BIG ? reinterpret_cast<float *>(smem_raw) : Xrows + size_t(G + 1) * Kp;   // row 0 = previous frame
     float *mscr = fvrows + size_t(G + 1) * kFvStride;
     float *rowsum = mscr + kWarps * B200AA_N_MEL;
     float *tparts = rowsum + ((G + 1 + 3) & ~3);

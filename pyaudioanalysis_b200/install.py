@@ -18,7 +18,7 @@ def install(pyaudioanalysis_pkg=None):
         ref_st, ref_mt = pyaudioanalysis_pkg.ShortTermFeatures, pyaudioanalysis_pkg.MidTermFeatures
     done = []
     for mod, ours, names in ((ref_st, ours_st, ("feature_extraction", "spectrogram", "chromagram")),
-                             (ref_mt, ours_mt, ("mid_feature_extraction", "directory_feature_extraction",
+                             (ref_mt, ours_mt, ("mid_feature_extraction", "beat_extraction", "directory_feature_extraction",
                                                 "multiple_directory_feature_extraction", "directory_feature_extraction_no_avg",
                                                 "mid_feature_extraction_to_file", "mid_feature_extraction_file_dir"))):
         for n in names:
