@@ -25,27 +25,8 @@ namespace b200aa {
 #ifndef B200AA_FAST_MINBLOCKS
 #define B200AA_FAST_MINBLOCKS 3   // CTAs per SM the fast kernel is compiled for (register budget)
 #endif
-// Experimental "lean" build (-DB200AA_FAST_LEAN=1, see scripts/build_variants.py): the run-staged feature kernels are
-// compiled for 4 CTAs per SM (64 registers) and put on a shared-memory diet to fit 56 KB per CTA -- twiddles and the
-// mel / DCT / chroma tables are read through L1 (__ldg) instead of being copied to shared memory, one carried |X| row
-// instead of two, 16-bit sign-flip words, no unused per-lane tables.  -DB200AA_FAST_LEAN=2 additionally shrinks those
-// CTAs to six warps (five transform warps + one spare; dense pass on four warps, mel / chroma on two): 4 CTAs per SM at
-// 80 registers.  Off by default: not yet measured on a B200.
-#ifndef B200AA_FAST_LEAN
-#define B200AA_FAST_LEAN 0
-#endif
-constexpr bool kLeanBuild = B200AA_FAST_LEAN != 0;
-__host__ __device__ constexpr bool fast_is_lean(bool runs, int mode) { return kLeanBuild && runs && mode == kModeFeatures; }
-__host__ __device__ constexpr int fast_min_blocks(bool runs, int mode) { return fast_is_lean(runs, mode) ? 4 : B200AA_FAST_MINBLOCKS; }
-// threads per CTA: one warp per frame slot, except the six-warp lean kernels
-__host__ __device__ constexpr int fast_threads(bool runs, int mode, int g) { return (B200AA_FAST_LEAN == 2 && fast_is_lean(runs, mode)) ? 192 : 32 * g; }
-// table element: shared memory (default) or global memory through the read-only L1 path (lean build)
-template <bool GL, typename T>
-__device__ __forceinline__ T tld(const T *p)
-{
-    if constexpr (GL) return __ldg(p);
-    else return *p;
-}
+// threads per CTA: one warp per frame slot
+__host__ __device__ constexpr int fast_threads(int g) { return 32 * g; }
 
 // ---- cheap math: MUFU-based reciprocal / rsqrt / log2 (2 ulp); the parity tolerance is 1e-4
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
@@ -243,8 +224,8 @@ __device__ __forceinline__ void spectral_features_h(const float *X, const float 
 }
 
 // time-domain rows of two frames per warp (half-warp each; lanes 0..9 of a half own the ten entropy blocks)
-template <int N, typename RF>
-__device__ __forceinline__ void time_features_runs_h(const float *runE, const RF *runF, float *fv, int l, bool active)
+template <int N>
+__device__ __forceinline__ void time_features_runs_h(const float *runE, const int *runF, float *fv, int l, bool active)
 {
     constexpr int RPB = N / 80;
     float e = 0.f;
@@ -275,7 +256,7 @@ __device__ __forceinline__ void time_features_runs_h(const float *runE, const RF
 // ---- mel + raw chroma on the upper half of the CTA (threads NT/2 .. NT-1) while the lower half runs the dense
 // pass: 16 threads per frame, every thread a group of <= 3 filters with balanced tap totals; then 12 threads per
 // frame for the chroma tap sums
-template <int G, bool GL = false, int UT = 16 * G>
+template <int G, int UT = 16 * G>
 __device__ __forceinline__ void upper_mel_chroma(const float *Xrows, int Kp, int ng, const SmallTables &tb, const int *grp_tab,
                                                  float *ms, float *chr, int t0)
 {
@@ -289,12 +270,12 @@ __device__ __forceinline__ void upper_mel_chroma(const float *Xrows, int Kp, int
             const float *X = Xrows + size_t(f) * Kp;
 #pragma unroll
             for (int h = 0; h < 3; ++h) {
-                const int i = tld<GL>(grp_tab + 3 * sub + h);
+                const int i = grp_tab[3 * sub + h];
                 if (i >= 0) {
-                    const int s0 = tld<GL>(tb.mel_start + i), cnt = tld<GL>(tb.mel_count + i), off = tld<GL>(tb.mel_off + i);
+                    const int s0 = tb.mel_start[i], cnt = tb.mel_count[i], off = tb.mel_off[i];
                     float acc = 0.f;
 #pragma unroll 4
-                    for (int q = 0; q < cnt; ++q) acc = fmaf(X[s0 + q], tld<GL>(tb.mel_w + off + q), acc);
+                    for (int q = 0; q < cnt; ++q) acc = fmaf(X[s0 + q], tb.mel_w[off + q], acc);
                     ms[f * B200AA_N_MEL + i] = 0.30102999566398120f * flog2(acc + B200AA_EPS);   // log10
                 }
             }
@@ -307,11 +288,11 @@ __device__ __forceinline__ void upper_mel_chroma(const float *Xrows, int Kp, int
         const int f = t / 12, c = t - f * 12;
         if (f < ng) {
             const float *X = Xrows + size_t(f) * Kp;
-            const int e0 = tld<GL>(tb.chr_off + c), e1 = tld<GL>(tb.chr_off + c + 1);
+            const int e0 = tb.chr_off[c], e1 = tb.chr_off[c + 1];
             float acc = 0.f;
             for (int e = e0; e < e1; ++e) {
-                const float v = X[tld<GL>(tb.chr_bin + e)];
-                acc = fmaf(v * v, tld<GL>(tb.chr_w + e), acc);
+                const float v = X[tb.chr_bin[e]];
+                acc = fmaf(v * v, tb.chr_w[e], acc);
             }
             chr[f * 12 + c] = acc;
         }
@@ -336,7 +317,7 @@ __device__ __forceinline__ void chroma_finalize_h(const float *chroma_raw, float
 //   y_c = sum_{n<20} D[c][n] * ((m_n - k) + (-1)^c (m_{39-n} - k)),  k = m_0 (any constant works for
 //   c >= 1 because those rows are orthogonal to constants; row 0 adds it back): keeps the float32 sum
 //   free of the large common offset of the log-mel values.
-template <int G, bool GL = false, int NT = 32 * G>
+template <int G, int NT = 32 * G>
 __device__ __forceinline__ void flat_dct(const float *ms, int ng, const SmallTables &tb, float *fvrows, int fbase, int tid0)
 {
     static_assert(NT % 2 == 0, "the two halves of a row sit in neighbouring lanes");
@@ -356,7 +337,7 @@ __device__ __forceinline__ void flat_dct(const float *ms, int ng, const SmallTab
         for (int j = 0; j < 10; ++j) {
             const int n = 10 * h + j;
             const float a = m[n] - kap, b = m[39 - n] - kap;
-            acc = fmaf(tld<GL>(row + n), fmaf(sgn, b, a), acc);
+            acc = fmaf(row[n], fmaf(sgn, b, a), acc);
         }
     }
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
@@ -378,9 +359,8 @@ __device__ __forceinline__ void flat_dct(const float *ms, int ng, const SmallTab
 // a frame are sums over its 100 runs and the 50 % overlap is computed once.
 // ----------------------------------------------------------------------------------------------
 
-template <typename RF>
 __device__ __forceinline__ void stage_run(const void *clip, int dtype, bool vec_ok, int64_t n0, const b200aa_clip_norm &nm,
-                                          float *dst, float *runE, RF *runF)
+                                          float *dst, float *runE, int *runF)
 {
     float d[8];
     if (dtype == B200AA_DTYPE_I16) {
@@ -427,7 +407,7 @@ __device__ __forceinline__ void stage_run(const void *clip, int dtype, bool vec_
     *reinterpret_cast<float4 *>(dst) = make_float4(d[0], d[1], d[2], d[3]);
     *reinterpret_cast<float4 *>(dst + 4) = make_float4(d[4], d[5], d[6], d[7]);
     *runE = e;
-    *runF = RF(fli | (link << 8));
+    *runF = fli | (link << 8);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -461,9 +441,8 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 }
 
 // stage_run() with the 8 int16 samples (and their predecessor) already in shared memory
-template <typename RF>
 __device__ __forceinline__ void stage_run_smem(const short *raw8, bool has_pred, const b200aa_clip_norm &nm, float *dst, float *runE,
-                                               RF *runF)
+                                               int *runF)
 {
     const int4 q = *reinterpret_cast<const int4 *>(raw8);
     const int w4[4] = {q.x, q.y, q.z, q.w};
@@ -486,7 +465,7 @@ __device__ __forceinline__ void stage_run_smem(const short *raw8, bool has_pred,
     *reinterpret_cast<float4 *>(dst) = make_float4(d[0], d[1], d[2], d[3]);
     *reinterpret_cast<float4 *>(dst + 4) = make_float4(d[4], d[5], d[6], d[7]);
     *runE = e;
-    *runF = RF(int(fl) | (int(linkf) << 8));
+    *runF = int(fl) | (int(linkf) << 8);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -524,20 +503,20 @@ struct FastShape {
     static constexpr int NT = 32 * G;            // threads per CTA
 };
 
-// fixed-size part of the CTA's shared memory (compile-time offsets); LEAN = the 4-CTAs-per-SM layout of the lean build
-template <int R1, int R2, int G, bool LEAN = false>
+// fixed-size part of the CTA's shared memory (compile-time offsets)
+template <int R1, int R2, int G>
 struct alignas(16) FastFixed {
     using S = FastShape<R1, R2, G>;
     float2 E[G * R1 * S::ES];              // transpose buffer [G][R][ES]; the |X| rows alias it
-    float2 tw[LEAN ? 2 : R1 * R2];        // W_Nc^(k1 n2)  [k1][n2]   (lean: read from global memory)
-    float2 twp[LEAN ? 2 : ((S::Nc / 2 + 2) & ~1)];     // W_N^k
-    alignas(16) float Xprev[(LEAN ? 1 : 2) * S::Kp];   // |X| of the previous step's last frame (double-buffered; lean: one row, copied in the store phase)
+    float2 tw[R1 * R2];                   // W_Nc^(k1 n2)  [k1][n2]
+    float2 twp[(S::Nc / 2 + 2) & ~1];     // W_N^k
+    alignas(16) float Xprev[2 * S::Kp];   // |X| of the previous step's last frame (double-buffered)
     float fvrows[(G + 1) * kFvStride];    // ring of feature rows: 34 features + the row's sum(X) in slot 34
     float mscr[G * B200AA_N_MEL];         // log-mel energies
     float chr[G * 12];                    // raw chroma sums
-    float parts[LEAN ? G * 32 : G * 64];  // entropy parts per (dense) half-warp; the chunked time-domain pass needs 64 per warp
-    alignas(16) int dlane[(LEAN ? 16 : 32) * 4];        // per-lane constants of the dense pass
-    alignas(16) int4 tlane[LEAN ? 1 : 32];              // per-lane constants of the chunked time-domain pass (non-run kernels)
+    float parts[G * 64];                  // entropy parts per (dense) half-warp; the chunked time-domain pass needs 64 per warp
+    alignas(16) int dlane[32 * 4];        // per-lane constants of the dense pass
+    alignas(16) int4 tlane[32];           // per-lane constants of the chunked time-domain pass (non-run kernels)
     unsigned int next_item;
     alignas(8) unsigned long long mbar;   // completion barrier of the TMA prefetch
 };
@@ -545,18 +524,12 @@ struct alignas(16) FastFixed {
 template <int R1, int R2, int G>
 inline size_t fast_fixed_bytes() { return sizeof(FastFixed<R1, R2, G>); }
 template <int R1, int R2, int G>
-inline size_t fast_smem_bytes(int step, int blob_words, bool runs, bool lean = false)
+inline size_t fast_smem_bytes(int step, int blob_words, bool runs)
 {
     using S = FastShape<R1, R2, G>;
     const size_t span_max = size_t(G - 1) * step + S::N;
     // see the kernel: with run staging the carried tail must survive, otherwise the whole span is dead after pass 1
     const bool zs_alias = runs ? size_t(G) * step >= 2 * size_t(G) * S::ZS : span_max >= 2 * size_t(G) * S::ZS;
-    if (lean) {     // no table blob, 16-bit flip words (run count padded to 8 so the sample span stays 16-byte aligned)
-        const size_t nrun8 = (span_max / 8 + 8) & ~size_t(7);
-        return sizeof(FastFixed<R1, R2, G, true>) + (sizeof(float) + sizeof(unsigned short)) * nrun8 +
-               sizeof(float) * (span_max + 8) + (zs_alias ? 0 : sizeof(float2) * G * S::ZS) +
-               sizeof(short) * (size_t(G) * step + 16);
-    }
     const size_t nrun = (span_max / 8 + 4) & ~size_t(3);
     return fast_fixed_bytes<R1, R2, G>() + sizeof(int) * ((blob_words + 3) & ~3) + 2 * sizeof(float) * nrun +
            sizeof(float) * (span_max + 8) + (zs_alias ? 0 : sizeof(float2) * G * S::ZS) +
@@ -564,34 +537,32 @@ inline size_t fast_smem_bytes(int step, int blob_words, bool runs, bool lean = f
 }
 
 template <int R1, int R2, int G, bool STEP_EVEN, bool RUNS, int MODE>
-__global__ void __launch_bounds__(fast_threads(RUNS, MODE, G), fast_min_blocks(RUNS, MODE)) st_fast_kernel(const StParams p, const float2 *__restrict__ g_tw,
+__global__ void __launch_bounds__(fast_threads(G), B200AA_FAST_MINBLOCKS) st_fast_kernel(const StParams p, const float2 *__restrict__ g_tw,
                                                                 const float2 *__restrict__ g_twp, unsigned int *work_counter)
 {
     using S = FastShape<R1, R2, G>;
     constexpr int Nc = S::Nc, N = S::N, K = S::K, Kp = S::Kp, ES = S::ES, H = S::H, ZS = S::ZS, TPF = S::TPF;
-    constexpr int NT = fast_threads(RUNS, MODE, G);      // 32 * G, or six warps in the LEAN=2 build
-    constexpr bool LEAN = fast_is_lean(RUNS, MODE);
-    static_assert(NT == S::NT || LEAN, "only the lean feature kernels run with fewer warps than frame slots");
+    constexpr int NT = fast_threads(G);
+    static_assert(NT == S::NT, "one warp per frame slot");
     static_assert(NT >= S::FftThreads && NT >= 16 * G + 32, "transform threads, and at least one warp next to the dense pass");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int step = p.step;
     // shared-memory layout: all fixed-size arrays sit at compile-time offsets (no address arithmetic to keep
     // live in registers); the three arrays whose size depends on the hop come last
-    using Fixed = FastFixed<R1, R2, G, LEAN>;
+    using Fixed = FastFixed<R1, R2, G>;
     Fixed &sm = *reinterpret_cast<Fixed *>(smem_raw);
     float2 *const E = sm.E, *const s_tw = sm.tw, *const s_twp = sm.twp;
     float *const Xprev = sm.Xprev, *const fvrows = sm.fvrows, *const mscr = sm.mscr, *const chr = sm.chr;
     float *const parts = sm.parts;
     int *const blob_s = reinterpret_cast<int *>(smem_raw + sizeof(Fixed));
-    const int blob_pad = LEAN ? 0 : (p.bl.words + 3) & ~3;
-    const int nrun = LEAN ? (((G - 1) * step + N) / 8 + 8 & ~7) : (((G - 1) * step + N) / 8 + 4 & ~3);
-    using runf_t = std::conditional_t<LEAN, unsigned short, int>;                     // sign-flip word of a run
+    const int blob_pad = (p.bl.words + 3) & ~3;
+    const int nrun = ((G - 1) * step + N) / 8 + 4 & ~3;
+    using runf_t = int;                                                               // sign-flip word of a run
     float *const runE = reinterpret_cast<float *>(blob_s + blob_pad);                 // run partials (RUNS only)
     runf_t *const runF = reinterpret_cast<runf_t *>(runE + nrun);
     float *const sS = reinterpret_cast<float *>(runF + nrun);                         // sample span
-    // twiddles: shared memory, or (lean) global memory through L1
-    auto TW = [&](int i) -> float2 { if constexpr (LEAN) return __ldg(g_tw + i); else return s_tw[i]; };
-    auto TWP = [&](int i) -> float2 { if constexpr (LEAN) return __ldg(g_twp + i); else return s_twp[i]; };
+    auto TW = [&](int i) -> float2 { return s_tw[i]; };
+    auto TWP = [&](int i) -> float2 { return s_twp[i]; };
     // published second-pass outputs [G][ZS]: the float samples of the G frames are dead once pass 1 has read them
     // (with run staging only the tail that the next step reuses must survive; without it the time-domain rows are
     // produced right after staging), so Zs lives on top of them
@@ -605,22 +576,18 @@ __global__ void __launch_bounds__(fast_threads(RUNS, MODE, G), fast_min_blocks(R
     static_assert((G & (G - 1)) == 0, "tile mapping");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if constexpr (!LEAN) {
-        for (int i = tid; i < p.bl.words; i += NT) blob_s[i] = p.blob[i];
-        for (int i = tid; i < R1 * R2; i += NT) s_tw[i] = g_tw[i];
-        for (int i = tid; i < Nc / 2 + 1; i += NT) s_twp[i] = g_twp[i];
-        __syncthreads();
-    }
-    const int *const blob_t = LEAN ? p.blob : blob_s;       // where the small tables are read from
+    for (int i = tid; i < p.bl.words; i += NT) blob_s[i] = p.blob[i];
+    for (int i = tid; i < R1 * R2; i += NT) s_tw[i] = g_tw[i];
+    for (int i = tid; i < Nc / 2 + 1; i += NT) s_twp[i] = g_twp[i];
+    __syncthreads();
+    const int *const blob_t = blob_s;
     const SmallTables tb = bind_tables(blob_t, p.bl);
-    if constexpr (!LEAN) {
-        if (tid < 32) sm.tlane[tid] = time_lane_init(N, tid);
-    }
+    if (tid < 32) sm.tlane[tid] = time_lane_init(N, tid);
     if (tid < 16) {
         const DenseLane d0_ = dense_lane_init_h<K>(tid);
         sm.dlane[tid * 4 + 0] = d0_.split; sm.dlane[tid * 4 + 1] = d0_.ps; sm.dlane[tid * 4 + 2] = d0_.pe;
     }
-    for (int i = tid; i < (LEAN ? 1 : 2) * Kp; i += NT) Xprev[i] = 0.f;
+    for (int i = tid; i < 2 * Kp; i += NT) Xprev[i] = 0.f;
     if (RUNS && tid == 0) mbar_init(&sm.mbar, 1);
     unsigned tma_phase = 0;       // parity of the next completion to wait for
     __syncthreads();
@@ -829,7 +796,7 @@ __global__ void __launch_bounds__(fast_threads(RUNS, MODE, G), fast_min_blocks(R
             if (rr > G) rr -= G + 1;
             float *fv = fvrows + rr * kFvStride;
             if (warp >= G / 2) {
-                upper_mel_chroma<G, LEAN, NT - 16 * G>(Xrows, Kp, ng, tb, blob_t + p.bl.mel_grp, mscr, chr, tid - 16 * G);
+                upper_mel_chroma<G, NT - 16 * G>(Xrows, Kp, ng, tb, blob_t + p.bl.mel_grp, mscr, chr, tid - 16 * G);
             } else {
                 const fidx_t fr = g0 + f;
                 const float *X = Xrows + size_t(f) * Kp;
@@ -839,11 +806,11 @@ __global__ void __launch_bounds__(fast_threads(RUNS, MODE, G), fast_min_blocks(R
                 const float rs = row_sum_h<K>(Xp, l16);
                 const float sxp = (has_prev && f == 0) ? fvrows[fbase * kFvStride + 34] : rs;
                 spectral_features_h<K>(X, Xp, sxp, sm.dlane + l16 * 4, parts + (warp * 2 + half) * 32, fv, l16, act,
-                                       (!LEAN && act && f == ng - 1) ? Xprev + (xsel ^ 1) * Kp : nullptr);
+                                       (act && f == ng - 1) ? Xprev + (xsel ^ 1) * Kp : nullptr);
             }
             __syncthreads();
             // ---- phase B: DCT rows (all threads), then chroma normalisation (lower half) / time-domain rows (upper half)
-            flat_dct<G, LEAN, NT>(mscr, ng, tb, fvrows, fbase, tid);
+            flat_dct<G, NT>(mscr, ng, tb, fvrows, fbase, tid);
             if (warp >= G / 2) {
                 if (RUNS) {
                     // the NT/32 - G/2 upper warps take the frames two at a time (one round when every frame pair has a warp)
@@ -863,15 +830,6 @@ __global__ void __launch_bounds__(fast_threads(RUNS, MODE, G), fast_min_blocks(R
                 chroma_finalize_h(chr + f * 12, fv, l16, act);
             }
             __syncthreads();
-            if constexpr (LEAN) {
-                // single carried |X| row: its readers (this step's dense pass) are behind the barriers above, the next
-                // ones run after the next step's transform; the rows themselves stay intact until that step's pass 1
-                static_assert(Kp % 4 == 0 && Kp / 4 <= NT, "carry-row copy mapping");
-                if (tid >= NT - Kp / 4) {
-                    const int i = tid - (NT - Kp / 4);
-                    reinterpret_cast<float4 *>(Xprev)[i] = reinterpret_cast<const float4 *>(Xrows + size_t(ng - 1) * Kp)[i];
-                }
-            }
             // ---- store the [n_out x 8] tile: 8 consecutive threads -> 8 consecutive frames of one feature row
             float *const out_b = p.out + size_t(b) * p.n_out * p.t_stride + g0;
             for (int e = tid; e < p.n_out * G; e += NT) {
@@ -894,7 +852,7 @@ __global__ void __launch_bounds__(fast_threads(RUNS, MODE, G), fast_min_blocks(R
             // (no copies, no barrier: the next step's writers of these arrays run several barriers later)
             fbase += ng;
             if (fbase > G) fbase -= G + 1;
-            if constexpr (!LEAN) xsel ^= 1;
+            xsel ^= 1;
         }
         } while (0);
         __syncthreads();
@@ -954,8 +912,8 @@ inline int fast_plan_init(int fs, int window, int step, const std::vector<int> &
 template <int R1, int R2, int G, bool EVEN, bool RUNS, int MODE>
 inline int fast_launch_t(const FastTables &ft, StParams p, int sm_count, int64_t T, cudaStream_t st)
 {
-    constexpr int NT = fast_threads(RUNS, MODE, G);
-    const size_t smem = fast_smem_bytes<R1, R2, G>(p.step, p.bl.words, RUNS, fast_is_lean(RUNS, MODE));
+    constexpr int NT = fast_threads(G);
+    const size_t smem = fast_smem_bytes<R1, R2, G>(p.step, p.bl.words, RUNS);
     if (smem > 110u * 1024u) return B200AA_ERR_UNSUPPORTED;      // very large hop: leave it to the generic kernel
     auto kern = st_fast_kernel<R1, R2, G, EVEN, RUNS, MODE>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200AA_ERR_CUDA;

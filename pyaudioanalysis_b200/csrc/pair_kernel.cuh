@@ -1,4 +1,5 @@
-// Warp-autonomous short-term kernel for windows N = 32 * R (R = 10, 15, 20, 25, 30: 320 / 480 / 640 / 800 / 960 samples).
+// Warp-autonomous short-term kernel for windows N = 32 * R (R = 10, 15, 16, 20, 25, 30, 32: 320 / 480 / 512 / 640 / 800 / 960 /
+// 1024 samples).
 //
 // One WARP owns a run of consecutive frames of one clip and processes them two at a time with no CTA-wide barrier:
 //   * frames a = 2q and b = 2q + 1 ride through ONE complex FFT of length N: z[n] = sa (xa[n] - xa[0]) + i sb (xb[n] - xb[0])
@@ -26,8 +27,11 @@
 
 namespace b200aa {
 
-constexpr int kPairWarps = 8;        // warps per CTA (each one autonomous)
-constexpr int kPairMinBlocks = 2;    // 2 x 8 warps per SM at <= 128 registers
+#ifndef B200AA_PAIR_MAXWARPS
+#define B200AA_PAIR_MAXWARPS 8
+#endif
+constexpr int kPairMaxWarps = B200AA_PAIR_MAXWARPS;     // warps per CTA (each one autonomous); fewer for the longest windows (shared memory)
+constexpr int kPairMinBlocks = 2;    // 2 CTAs per SM: 16 warps at <= 128 registers
 
 template <int R>
 struct PairShape {
@@ -38,7 +42,10 @@ struct PairShape {
     static constexpr int TZ = (R * LS > N + 2) ? R * LS : N + 2;   // float2 elements of the transform buffer
     static constexpr int Lt = N / 10;                // energy-entropy block length (ShortTermFeatures.py:41)
     static constexpr bool kShareable = (N % 160) == 0;    // half a frame = 5 whole blocks, rows split at lane 0 / 16 only
-    static_assert(2 * TZ >= Kp, "the |X| row of frame a fits the transform buffer");
+    // after the separation the transform buffer holds the |X| row of frame a (Kp floats) and, behind it, the mel scratch:
+    // filter outputs, their log10, and the folded halves for the DCT ([f][0..19] sums, [f][20..39] differences), 2 x 40 each
+    static constexpr int MS0 = (Kp + 3) & ~3;
+    static_assert(2 * TZ >= MS0 + 6 * B200AA_N_MEL, "|X| row of frame a + mel scratch fit the transform buffer");
     static_assert(Lt >= 32, "a 32-sample row touches two blocks at most");
 };
 
@@ -48,19 +55,26 @@ struct alignas(16) PairWarpMem {
     float2 tz[S::TZ];                       // pass-1 outputs, planes re[k1][LS] | im[k1][LS]  ->  Z[k] (natural order, Z[N] = Z[0])  ->  |X| row of a
     alignas(16) float rowb[2][S::Kp];       // |X| rows of frame b: this step's and the previous step's (alternating)
     float fv[9 * kFvStride];                // feature rows: row 0 = the frame before the tile, rows 1..8 = the tile
-    float msraw[2 * B200AA_N_MEL];          // mel filter outputs of a, b
-    float ms[2 * B200AA_N_MEL];             // log10 of them
-    float mfold[2 * B200AA_N_MEL];          // folded halves for the DCT: [f][0..19] sums, [f][20..39] differences
     float chr[2 * 12];                      // raw chroma sums
     float parts[2 * 32];                    // spectral-entropy parts of the dense pass
     float blk[24];                          // block energies: a -> [0, 10), b -> [5, 15) (shared halves) or [10, 20); rests at 20, 21
 };
 
+// warps per CTA such that two CTAs fit the 227 KB of an SM (per CTA: 113 KB cap of pair_launch_t, twiddles, lane
+// constants, up to 6.5 KB of mel / DCT / chroma tables)
+template <int R>
+__host__ __device__ constexpr int pair_warps()
+{
+    constexpr int budget = 113 * 1024 - R * 32 * 8 - 256 - 6656;
+    constexpr int w = budget / int(sizeof(PairWarpMem<R>));
+    return w > kPairMaxWarps ? kPairMaxWarps : (w < 2 ? 2 : w);
+}
+
 template <int R>
 struct alignas(16) PairCtaMem {
     float2 tw[R * 32];                      // W_N^(k1 n2), [k1][n2]
     alignas(16) int dlane[16 * 4];          // per-lane constants of the dense pass
-    PairWarpMem<R> w[kPairWarps];
+    PairWarpMem<R> w[pair_warps<R>()];
 };
 
 // constant tables of the pair kernel (int32 words, copied to shared memory once per CTA)
@@ -100,13 +114,34 @@ __device__ __forceinline__ float fsqrt_fast(float x)        // MUFU.SQRT (2 ulp,
 // frame's row sum taken from where it already exists -- half 1 (frame b) receives half 0's (frame a's) sum by shuffle,
 // half 0 the carried sum of the previous pair's b -- instead of re-reading the previous row.
 // ----------------------------------------------------------------------------------------------
+// per-lane constants: .x = bins of the lane's chunk that belong to the earlier entropy block, [.y, .z) = parts of block l
+template <int K>
+__device__ __forceinline__ int4 pair_lane_init(int l)
+{
+    constexpr int CB = 2 * (((K + 31) / 32) | 1), Lb = K / 10;
+    const int k0 = l * CB;
+    const int bnd = ((k0 + CB - 1) / Lb) * Lb;
+    int4 d;
+    d.x = bnd > k0 ? bnd - k0 : 0;
+    int ps = 32, pe = 0;
+    for (int q = 0; q < 16; ++q) {
+        const int b0 = q * CB, bb = ((b0 + CB - 1) / Lb) * Lb, sp = bb > b0 ? bb - b0 : 0;
+        if (sp > 0 && b0 >= l * Lb && b0 + sp <= (l + 1) * Lb) { ps = min(ps, 2 * q); pe = max(pe, 2 * q + 1); }
+        if (b0 + sp >= l * Lb && b0 + CB <= (l + 1) * Lb) { ps = min(ps, 2 * q + 1); pe = max(pe, 2 * q + 2); }
+    }
+    if (l >= 10) { ps = 0; pe = 0; }
+    d.y = ps; d.z = pe; d.w = 0;
+    return d;
+}
+
 template <int K>
 __device__ __forceinline__ void pair_spectral(const float *X, const float *Xp, float sxp_carried, bool own_prev, const int *dlp,
                                               float *parts, float *fv, int l, int half)
 {
-    constexpr int C2 = HalfShape<K>::C2, CB = HalfShape<K>::CB;
+    constexpr int C2 = ((K + 31) / 32) | 1, CB = 2 * C2, Lb = K / 10;
+    static_assert(CB < Lb, "one entropy block boundary per lane at most");
     const int k0 = l * CB;
-    const int4 dlv = *reinterpret_cast<const int4 *>(dlp);        // {split (pairs), ps, pe, -}
+    const int4 dlv = *reinterpret_cast<const int4 *>(dlp);        // {split (bins), ps, pe, -}
     const float2 *X2 = reinterpret_cast<const float2 *>(X) + l * C2;
     const float2 *Xp2 = reinterpret_cast<const float2 *>(Xp) + l * C2;
     float2 x2[C2];
@@ -121,7 +156,13 @@ __device__ __forceinline__ void pair_spectral(const float *X, const float *Xp, f
         s1 = fmaf(float(2 * j + 1), t, s1);
         sb += x2[j].y;
         const float2 sq = __fmul2_rn(x2[j], x2[j]);
-        if (j < dlv.x) plo2 = f2add(plo2, sq); else phi2 = f2add(phi2, sq);
+        if constexpr ((Lb % 2) == 0) {                   // block boundaries fall between (even, odd) bin pairs
+            if (2 * j < dlv.x) plo2 = f2add(plo2, sq); else phi2 = f2add(phi2, sq);
+        } else {                                         // power-of-two windows: a boundary may split a pair
+            const float2 m = make_float2(2 * j < dlv.x ? 1.f : 0.f, 2 * j + 1 < dlv.x ? 1.f : 0.f);
+            plo2 = __ffma2_rn(sq, m, plo2);
+            phi2 = __ffma2_rn(sq, make_float2(1.f - m.x, 1.f - m.y), phi2);
+        }
     }
     const float plo = plo2.x + plo2.y, phi = phi2.x + phi2.y, part = plo + phi;
     float sk = fmaf(float(k0), sx, s1 + sb);         // sum (k0 + i + 1) x_i
@@ -171,7 +212,7 @@ __device__ __forceinline__ void pair_spectral(const float *X, const float *Xp, f
     const float sp = sp2.x + sp2.y, fl = fl2.x + fl2.y;
     __syncwarp();
     float e = 0.f;
-    constexpr int MAXP = 2 * (HalfShape<K>::Lb / CB + 2);
+    constexpr int MAXP = 2 * (Lb / CB + 2);
 #pragma unroll
     for (int q = 0; q < MAXP; ++q) e += (dlv.y + q < dlv.z) ? parts[dlv.y + q] : 0.f;
     float ent = 0.f;
@@ -325,7 +366,7 @@ __device__ __forceinline__ void frame_scale(float E, float inv_a2n, float &s, fl
 // kernel
 // ----------------------------------------------------------------------------------------------
 template <int R, bool SHARED>
-__global__ void __launch_bounds__(32 * kPairWarps, kPairMinBlocks) st_pair_kernel(const PairParams pp)
+__global__ void __launch_bounds__(32 * pair_warps<R>(), kPairMinBlocks) st_pair_kernel(const PairParams pp)
 {
     using S = PairShape<R>;
     constexpr int N = S::N, K = S::K, Kp = S::Kp, C = S::C, JK = S::JK, LS = S::LS;
@@ -335,12 +376,10 @@ __global__ void __launch_bounds__(32 * kPairWarps, kPairMinBlocks) st_pair_kerne
     int *const blob_s = reinterpret_cast<int *>(smem_raw + sizeof(PairCtaMem<R>));
     const StParams &p = pp.st;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < pp.pbl.words; i += 32 * kPairWarps) blob_s[i] = pp.pblob[i];
-    for (int i = tid; i < R * 32; i += 32 * kPairWarps) cm_.tw[i] = pp.tw[i];
-    if (tid < 16) {
-        const DenseLane d0_ = dense_lane_init_h<K>(tid);
-        cm_.dlane[tid * 4 + 0] = d0_.split; cm_.dlane[tid * 4 + 1] = d0_.ps; cm_.dlane[tid * 4 + 2] = d0_.pe; cm_.dlane[tid * 4 + 3] = 0;
-    }
+    constexpr int NTHR = 32 * pair_warps<R>();
+    for (int i = tid; i < pp.pbl.words; i += NTHR) blob_s[i] = pp.pblob[i];
+    for (int i = tid; i < R * 32; i += NTHR) cm_.tw[i] = pp.tw[i];
+    if (tid < 16) *reinterpret_cast<int4 *>(cm_.dlane + tid * 4) = pair_lane_init<K>(tid);
     __syncthreads();
     const float *const t_dct = reinterpret_cast<const float *>(blob_s + pp.pbl.dct);
     const int *const t_mrec = blob_s + pp.pbl.mel_rec;
@@ -350,6 +389,7 @@ __global__ void __launch_bounds__(32 * kPairWarps, kPairMinBlocks) st_pair_kerne
     PairWarpMem<R> &wm = cm_.w[warp];
     float *const rowa = reinterpret_cast<float *>(wm.tz);
     float *const t_re = reinterpret_cast<float *>(wm.tz), *const t_im = t_re + R * LS;
+    float *const msraw = rowa + S::MS0, *const mslog = msraw + 2 * B200AA_N_MEL, *const mfold = mslog + 2 * B200AA_N_MEL;
     const int step = p.step;
     const int half = lane >> 4, l16 = lane & 15;
     const unsigned FULLM = 0xffffffffu;
@@ -607,7 +647,7 @@ __global__ void __launch_bounds__(32 * kPairWarps, kPairMinBlocks) st_pair_kerne
                     acc = fmaf(xp[1], w.y, acc);
                     acc = fmaf(xp[2], w.z, acc);
                     acc = fmaf(xp[3], w.w, acc);
-                    if (rec & (1 << 24)) { wm.msraw[half * B200AA_N_MEL + ((rec >> 16) & 0xff)] = acc; acc = 0.f; }
+                    if (rec & (1 << 24)) { msraw[half * B200AA_N_MEL + ((rec >> 16) & 0xff)] = acc; acc = 0.f; }
                 }
                 float ch = 0.f;
                 for (int t = 0; t < CT; ++t) {
@@ -620,25 +660,25 @@ __global__ void __launch_bounds__(32 * kPairWarps, kPairMinBlocks) st_pair_kerne
             __syncwarp();
             // ---- log10, fold (m_n - k) +- (m_(39-n) - k) with k = m_0 (see flat_dct in fast_kernel.cuh), 13 x 20 DCT rows
 #pragma unroll
-            for (int t = lane; t < 2 * B200AA_N_MEL; t += 32) wm.ms[t] = 0.30102999566398120f * flog2(wm.msraw[t] + B200AA_EPS);
+            for (int t = lane; t < 2 * B200AA_N_MEL; t += 32) mslog[t] = 0.30102999566398120f * flog2(msraw[t] + B200AA_EPS);
             __syncwarp();
 #pragma unroll
             for (int t = lane; t < 2 * B200AA_N_MEL; t += 32) {
                 const int f = t >= B200AA_N_MEL ? 1 : 0, r = t - f * B200AA_N_MEL;
                 const int kind = r >= 20 ? 1 : 0, n = r - 20 * kind;
-                const float *m = wm.ms + f * B200AA_N_MEL;
+                const float *m = mslog + f * B200AA_N_MEL;
                 const float a = m[n], bq = m[39 - n], kap = m[0];
-                wm.mfold[t] = kind ? a - bq : (a - kap) + (bq - kap);
+                mfold[t] = kind ? a - bq : (a - kap) + (bq - kap);
             }
             __syncwarp();
             {
                 const int c = l16 < B200AA_N_MFCC ? l16 : 0;
-                const float *src = wm.mfold + half * B200AA_N_MEL + 20 * (c & 1);
+                const float *src = mfold + half * B200AA_N_MEL + 20 * (c & 1);
                 const float *row = t_dct + c * 41;
                 float acc = 0.f;
 #pragma unroll
                 for (int n = 0; n < 20; ++n) acc = fmaf(row[n], src[n], acc);
-                if (c == 0) acc = fmaf(6.324555320336759f, wm.ms[half * B200AA_N_MEL], acc);      // sqrt(1/40) * 40 * k
+                if (c == 0) acc = fmaf(6.324555320336759f, mslog[half * B200AA_N_MEL], acc);      // sqrt(1/40) * 40 * k
                 if (l16 < B200AA_N_MFCC) (half ? fvb : fva)[8 + c] = acc;
             }
             chroma_finalize_h(wm.chr + half * 12, half ? fvb : fva, l16, true);
@@ -686,9 +726,11 @@ inline int pair_r_for_window(int window)
     switch (window) {
     case 320: return 10;
     case 480: return 15;
+    case 512: return 16;
     case 640: return 20;
     case 800: return 25;
     case 960: return 30;
+    case 1024: return 32;
     default: return 0;
     }
 }
@@ -818,7 +860,7 @@ inline int pair_launch_t(const PairTables &pt, const StParams &p, int sm_count, 
     auto kern = st_pair_kernel<R, SHARED>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200AA_ERR_CUDA;
     int occ = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * kPairWarps, smem) != cudaSuccess) return B200AA_ERR_CUDA;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * pair_warps<R>(), smem) != cudaSuccess) return B200AA_ERR_CUDA;
     occ = occ < 1 ? 1 : occ;
     PairParams pp;
     pp.st = p;
@@ -828,6 +870,7 @@ inline int pair_launch_t(const PairTables &pt, const StParams &p, int sm_count, 
     pp.counter = counter;
     pp.dbg = dbg;
     const int64_t NP = (T + 1) / 2;                                  // pairs per (full-length) clip
+    constexpr int kPairWarps = pair_warps<R>();
     const int64_t slots = int64_t(sm_count) * occ * kPairWarps;      // resident warps
     const int64_t total = NP * p.n_clips;
     int64_t share = (total + slots - 1) / slots;                     // pairs per warp if perfectly balanced
@@ -877,6 +920,8 @@ inline int pair_launch_features(const PairTables &pt, const StParams &p, int sm_
     switch (pt.R) {
     case 10: return pair_launch_r<10>(pt, p, sm_count, T, counter, dbg, st);
     case 15: return pair_launch_r<15>(pt, p, sm_count, T, counter, dbg, st);
+    case 16: return pair_launch_r<16>(pt, p, sm_count, T, counter, dbg, st);
+    case 32: return pair_launch_r<32>(pt, p, sm_count, T, counter, dbg, st);
     case 20: return pair_launch_r<20>(pt, p, sm_count, T, counter, dbg, st);
     case 25: return pair_launch_r<25>(pt, p, sm_count, T, counter, dbg, st);
     case 30: return pair_launch_r<30>(pt, p, sm_count, T, counter, dbg, st);

@@ -1,19 +1,10 @@
-"""Build experimental variants of libb200aa.so next to the default one (A/B runs on the GPU box).
+"""Compile-time variants of libb200aa.so for A/B runs on the GPU box (the default library is untouched):
 
-    python scripts/build_variants.py            # all variants
-    python scripts/build_variants.py lean       # one
+    python scripts/build_variants.py pw6        # one
+    python scripts/build_variants.py            # all
+    gpurun -- 'python scripts/ab_run.py default pw6 | tee gpurun_out/ab.jsonl'
 
-Variants land in pyaudioanalysis_b200/variants/libb200aa_<name>.so (git-ignored like every .so, shipped to the
-GPU box by gpurun) and are selected per process with the B200AA_LIB environment variable.  One gpurun call A/Bs
-them (quick parity against the oracle + kernel timing per build):
-
-    gpurun --timeout 300 -- 'python scripts/ab_run.py default lean lean6 mb4 hostpipe | tee gpurun_out/ab.jsonl'
-
-and the full suite runs on a variant with `B200AA_LIB=$PWD/pyaudioanalysis_b200/variants/libb200aa_lean.so python -m
-pytest tests -m gpu -q`.
-
-The default build is never affected: every variant is a compile-time switch that is off by default (the SASS of
-the default library was compared before / after the switches were added).
+Variants land in pyaudioanalysis_b200/variants/libb200aa_<name>.so and are selected per process with B200AA_LIB.
 """
 import os
 import subprocess
@@ -24,17 +15,10 @@ sys.path.insert(0, ROOT)
 from pyaudioanalysis_b200 import build as B   # noqa: E402
 
 VARIANTS = {
-    # 4 CTAs / SM for the run-staged feature kernels: 64 registers, 56 KB shared memory (tables through L1,
-    # one carried |X| row, 16-bit flip words); see B200AA_FAST_LEAN in csrc/fast_kernel.cuh
-    "lean": ["-DB200AA_FAST_LEAN=1"],
-    # lean + six-warp CTAs (five transform warps + one spare, dense pass on four warps, mel / chroma on two):
-    # 4 CTAs / SM at 80 registers instead of 64
-    "lean6": ["-DB200AA_FAST_LEAN=2"],
-    # 64 registers / 4 CTAs per SM without the diet: only the small-window shapes (<= 45 KB: 320 / 400 / 480-sample
-    # windows) actually reach 4 CTAs per SM with it
+    # pair kernel with six warps per CTA: 12 warps per SM at up to 168 registers instead of 16 at 128
+    "pw6": ["-DB200AA_PAIR_MAXWARPS=6"],
+    # CTA kernel at 64 registers / 4 CTAs per SM
     "mb4": ["-DB200AA_FAST_MINBLOCKS=4"],
-    # b200aa_st_features_host as a chunked three-stream pipeline below the C ABI (end-to-end through the C entry point)
-    "hostpipe": ["-DB200AA_HOST_PIPELINE=1"],
     # reference points for bisecting: scalar butterflies / IEEE MUFU wrappers
     "nof32x2": ["-DB200AA_NO_F32X2"],
     "noftz": ["-DB200AA_NO_FTZ_MUFU"],

@@ -42,7 +42,7 @@ def main():
     ok = True
     cases = [(16000, 800, 400, 48000), (16000, 800, 400, 32400), (16000, 800, 200, 20000), (16000, 800, 800, 24000), (16000, 800, 333, 20000),
              (16000, 320, 160, 12000), (16000, 480, 240, 14000), (16000, 640, 320, 20000), (16000, 640, 160, 12000),
-             (16000, 960, 480, 30000), (48000, 960, 960, 40000), (8000, 320, 80, 8000), (16000, 800, 400, 800), (16000, 800, 400, 1200)]
+             (16000, 960, 480, 30000), (48000, 960, 960, 40000), (16000, 1024, 512, 30000), (16000, 512, 256, 20000), (16000, 1024, 256, 20000), (8000, 320, 80, 8000), (16000, 800, 400, 800), (16000, 800, 400, 1200)]
     for fs, w, s, n in cases:
         x = O.synth_clip(100 + w + s, n, fs)
         ref = O.feature_extraction(x, fs, w, s)[0]
@@ -111,6 +111,22 @@ def main():
         ms = e0.elapsed_time(e1) / 10
         print(json.dumps({"kernel": kind, "seg": env, "ms": ms, "Mframes_per_s": 399000 / ms / 1e3}))
     os.environ.pop("B200AA_PAIR_SEG", None)
+    for w, s_ in ((1024, 512), (512, 256), (640, 320), (960, 480), (320, 160)):
+        T = (160000 - w) // s_ + 1
+        o2 = torch.empty((1000, 68, T), device="cuda")
+        for kind in (2, 0):
+            pl = Plan(16000, w, s_).prefer_kernel(kind)
+            for _ in range(2):
+                pkg.feature_extraction_batch(c2, 16000, w, s_, out=o2, norm=norm, plan=pl)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                pkg.feature_extraction_batch(c2, 16000, w, s_, out=o2, norm=norm, plan=pl)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            print(json.dumps({"window": w, "step": s_, "kernel": pl.kernel_kind(), "ms": ms, "Mframes_per_s": 1000 * T / ms / 1e3}))
     print("ALL OK" if ok else "SOME BAD")
 
 

@@ -312,22 +312,33 @@ def test_mid_pool_kernel(P):
 
 
 def test_kernel_kinds_agree(P):
-    """Where a specialised kernel exists it must agree with the generic one (and both with the oracle)."""
+    """Every kernel that exists for a window (2 = warp-autonomous pair kernel, 1 = register-tiled CTA kernel, 0 = generic)
+    must agree with the oracle; the default plan picks the fastest one."""
     import torch
     from pyaudioanalysis_b200._lib import Plan
     for fs, w, s in [(16000, 800, 400), (44100, 882, 441), (16000, 800, 800), (16000, 800, 200), (8000, 400, 200),
-                     (16000, 400, 160), (16000, 480, 240), (8000, 600, 300), (16000, 640, 320), (16000, 320, 160)]:
-        clips = np.stack([O.synth_clip(40 + i, 24000, fs) for i in range(3)])
+                     (16000, 400, 160), (16000, 480, 240), (8000, 600, 300), (16000, 640, 320), (16000, 320, 160),
+                     (16000, 1024, 512), (16000, 512, 256), (16000, 512, 128), (48000, 960, 480), (16000, 1024, 300),
+                     (16000, 800, 333)]:
+        clips = np.stack([O.synth_clip(40 + i, 24000 + 7 * i, fs)[:24000] for i in range(3)])
         d = torch.from_numpy(clips).cuda()
-        pf, pg = Plan(fs, w, s), Plan(fs, w, s)
+        refs = [O.feature_extraction(clips[i], fs, w, s)[0] for i in range(3)]
+        kinds = set()
+        for prefer in (-1, 2, 1, 0):
+            pl = Plan(fs, w, s).prefer_kernel(prefer)
+            kind = pl.kernel_kind()
+            if prefer >= 0 and kind != prefer:
+                continue                        # that kernel does not exist for this window
+            kinds.add(kind)
+            got = P.feature_extraction_batch(d, fs, w, s, plan=pl).cpu().numpy()
+            for i in range(3):
+                check_features(got[i], refs[i], w // 2, f"kernel kind {kind} (prefer {prefer}) fs={fs} w={w} s={s}")
+        assert 0 in kinds
+        if w in (320, 480, 512, 640, 800, 960, 1024):
+            assert 2 in kinds and Plan(fs, w, s).kernel_kind() == 2
+        pg = Plan(fs, w, s)
         pg.force_generic(True)
-        a = P.feature_extraction_batch(d, fs, w, s, plan=pf).cpu().numpy()
-        b = P.feature_extraction_batch(d, fs, w, s, plan=pg).cpu().numpy()
         assert pg.kernel_kind() == 0
-        for i in range(3):
-            ref = O.feature_extraction(clips[i], fs, w, s)[0]
-            check_features(a[i], ref, w // 2, f"default kernel (kind {pf.kernel_kind()}) fs={fs} w={w} s={s}")
-            check_features(b[i], ref, w // 2, f"generic kernel fs={fs} w={w} s={s}")
 
 
 def test_row_kernels_agree(P):

@@ -1,8 +1,8 @@
-"""CPU: shared-memory budget of the fused kernel (csrc/fast_kernel.cuh) for the shapes the library instantiates.
+"""CPU: shared-memory budgets of the two feature kernels for the shapes the library instantiates.
 
 sm_100: 233 472 B of shared memory per SM, 1 024 B reserved per resident CTA, so n CTAs per SM need
-n * (bytes + 1024) <= 233 472.  The default layout is sized for 3 CTAs per SM on the headline shape, the lean
-layout (-DB200AA_FAST_LEAN=1, scripts/build_variants.py) for 4."""
+n * (bytes + 1024) <= 233 472.  The CTA kernel (csrc/fast_kernel.cuh) is sized for 3 CTAs per SM on the headline shape;
+the pair kernel (csrc/pair_kernel.cuh) runs 2 CTAs of up to 8 autonomous warps per SM."""
 import os
 import shutil
 import subprocess
@@ -30,16 +30,20 @@ def test_shared_memory_budget(tmp_path):
     res = subprocess.run([_nvcc(), "-std=c++17", "-arch=sm_100a", "-o", exe, os.path.join(ROOT, "tests", "smem_budget_host.cu")],
                          capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
-    rows = [tuple(int(v) for v in ln.split()) for ln in subprocess.run([exe], capture_output=True, text=True).stdout.splitlines()]
-    table = {(n, s): (runs, d, lean) for n, s, runs, d, lean in rows}
+    lines = [ln.split() for ln in subprocess.run([exe], capture_output=True, text=True).stdout.splitlines()]
+    table = {(int(l[1]), int(l[2])): (int(l[3]), int(l[4])) for l in lines if l[0] == "fast"}
     assert len(table) == 15
-    # headline shape (50 / 25 ms @ 16 kHz): 3 CTAs per SM by default, 4 with the lean layout
-    runs, d, lean = table[(800, 400)]
-    assert runs == 1 and ctas_per_sm(d) == 3 and ctas_per_sm(lean) >= 4
+    # headline shape (50 / 25 ms @ 16 kHz): 3 CTAs per SM
+    runs, d = table[(800, 400)]
+    assert runs == 1 and ctas_per_sm(d) == 3
     # every instantiated shape keeps at least 2 CTAs per SM at hop = window / 2 and fits the launcher's 110 KB cap
-    for (n, s), (runs, d, lean) in table.items():
+    for (n, s), (runs, d) in table.items():
         assert d <= 110 * 1024, (n, s, d)
         if 2 * s <= n:
             assert ctas_per_sm(d) >= 2, (n, s, d)
-        if runs:
-            assert lean < d
+    pair = {int(l[1]): (int(l[2]), int(l[3])) for l in lines if l[0] == "pair"}
+    assert set(pair) == {320, 480, 512, 640, 800, 960, 1024}
+    for w, (warps, nbytes) in pair.items():
+        assert ctas_per_sm(nbytes) >= 2 and nbytes <= 113 * 1024, (w, warps, nbytes)     # pair_launch_t's cap
+        assert warps >= 4
+    assert pair[800][0] == 8          # 16 autonomous warps per SM on the headline shape
