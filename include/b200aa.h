@@ -92,6 +92,9 @@ int  b200aa_plan_prefer_kernel(b200aa_plan *plan, int kind);
 /* force the generic kernel (testing): returns the previous setting */
 int  b200aa_plan_force_generic(b200aa_plan *plan, int on);
 
+/* frees the device workspaces the host entry points keep between calls (grown to the largest call seen) */
+int  b200aa_plan_trim(b200aa_plan *plan);
+
 /* ------------------------------------------------------------------ device entry points */
 
 /* Kernel 0: per-clip statistics -> normalisation records.

@@ -37,6 +37,7 @@ SIGNATURES = {
     "b200aa_plan_kernel_kind": (c_int, [c_vp]),
     "b200aa_plan_force_generic": (c_int, [c_vp, c_int]),
     "b200aa_plan_prefer_kernel": (c_int, [c_vp, c_int]),
+    "b200aa_plan_trim": (c_int, [c_vp]),
     "b200aa_debug_set_dump": (c_int, [c_vp]),
     "b200aa_clip_stats": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "b200aa_st_features": (c_int, [c_vp, c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_vp]),
@@ -114,6 +115,10 @@ class Plan:
         check(lib().b200aa_plan_prefer_kernel(self.handle, int(kind)))
         return self
 
+    def trim(self):
+        """Free the device workspaces the host entry points keep between calls."""
+        check(lib().b200aa_plan_trim(self.handle))
+
     def __del__(self):
         try:
             if getattr(self, "handle", None) and _lib is not None:
@@ -123,12 +128,15 @@ class Plan:
             pass
 
 
-_plans = {}
+import collections
+
+_plans = collections.OrderedDict()
 _plans_lock = threading.Lock()
+MAX_CACHED_PLANS = 32       # least recently used plans beyond this are dropped (their device tables and workspaces are freed)
 
 
 def get_plan(fs, window, step, device=None):
-    """Plans are cached per (device, fs, window, step)."""
+    """Plans are cached per (device, fs, window, step), least recently used first out."""
     if device is None:
         try:
             import torch
@@ -141,6 +149,10 @@ def get_plan(fs, window, step, device=None):
         if pl is None:
             pl = Plan(fs, window, step)
             _plans[key] = pl
+            while len(_plans) > MAX_CACHED_PLANS:
+                _plans.popitem(last=False)          # Plan.__del__ destroys it once no caller holds it any more
+        else:
+            _plans.move_to_end(key)
         return pl
 
 

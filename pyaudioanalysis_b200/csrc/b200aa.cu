@@ -144,8 +144,14 @@ struct b200aa_plan {
     FastTables fast{};                  // extra device tables of the specialised kernel
     PairTables pair{};                  // inter-pass twiddles of the warp-autonomous pair kernel (windows 32 * R)
     int prefer = -1;                    // -1 = automatic, 0 / 1 / 2 = generic / register-tiled / pair kernel only (testing, A/B)
-    unsigned int *d_counters = nullptr; // ring of work counters of the pair kernel (one per in-flight launch)
-    std::atomic<unsigned int> next_counter{0};
+    // ring of work counters (one per in-flight launch of a persistent kernel).  A slot is handed out again only after
+    // the launch that used it last has finished: that launch recorded the slot's event, the next user's stream waits on it.
+    static constexpr unsigned kSlots = 256;
+    unsigned int *d_counters = nullptr;
+    cudaEvent_t slot_event[kSlots] = {};
+    bool slot_used[kSlots] = {};
+    unsigned next_slot = 0;
+    std::mutex slot_mu;
     static constexpr int kPipe = 3;     // streams of the chunked host pipeline, each with its own clips / records / features buffers
     cudaStream_t pipe_stream[kPipe] = {nullptr, nullptr, nullptr};
     void *pipe_ws[kPipe][3] = {};
@@ -161,6 +167,7 @@ struct b200aa_plan {
         fast.release();
         pair.release();
         if (d_counters) cudaFree(d_counters);
+        for (cudaEvent_t e : slot_event) if (e) cudaEventDestroy(e);
     }
 };
 
@@ -303,12 +310,31 @@ extern "C" int b200aa_plan_create(b200aa_plan **out, int fs, int window, int ste
         rc = pair_plan_init(window, pblob, pbl, &pl->pair);
         if (rc != B200AA_OK) return cuda_fail(cudaGetLastError(), "pair_plan_init");
     }
-    CK(cudaMalloc(&pl->d_counters, kCounterRing * sizeof(unsigned int)));
+    CK(cudaMalloc(&pl->d_counters, b200aa_plan::kSlots * sizeof(unsigned int)));
     *out = pl.release();
     return B200AA_OK;
 }
 
 extern "C" void b200aa_plan_destroy(b200aa_plan *plan) { delete plan; }
+// work-counter slot for one launch on stream st (see b200aa_plan::slot_event); call slot_done after the launch
+static int slot_acquire(b200aa_plan *pl, cudaStream_t st, unsigned *slot, unsigned int **ctr)
+{
+    std::lock_guard<std::mutex> g(pl->slot_mu);
+    const unsigned s = pl->next_slot++ % b200aa_plan::kSlots;
+    if (!pl->slot_event[s]) CK(cudaEventCreateWithFlags(&pl->slot_event[s], cudaEventDisableTiming));
+    if (pl->slot_used[s]) CK(cudaStreamWaitEvent(st, pl->slot_event[s], 0));
+    *slot = s;
+    *ctr = pl->d_counters + s;
+    return B200AA_OK;
+}
+static int slot_done(b200aa_plan *pl, cudaStream_t st, unsigned slot)
+{
+    std::lock_guard<std::mutex> g(pl->slot_mu);
+    CK(cudaEventRecord(pl->slot_event[slot], st));
+    pl->slot_used[slot] = true;
+    return B200AA_OK;
+}
+
 static bool use_pair(const b200aa_plan *pl) { return pl->pair.R && !pl->force_generic && (pl->prefer < 0 || pl->prefer == 2); }
 static bool use_fast(const b200aa_plan *pl) { return pl->fast_kind && !pl->force_generic && (pl->prefer < 0 || pl->prefer == 1); }
 extern "C" int b200aa_plan_kernel_kind(const b200aa_plan *plan)
@@ -334,6 +360,23 @@ extern "C" int b200aa_plan_force_generic(b200aa_plan *plan, int on)
     int prev = plan->force_generic;
     plan->force_generic = on ? 1 : 0;
     return prev;
+}
+
+// free the grow-only workspaces of the host-buffer entry points (they are re-allocated on demand)
+extern "C" int b200aa_plan_trim(b200aa_plan *plan)
+{
+    if (!plan) return B200AA_ERR_INVALID;
+    std::lock_guard<std::mutex> g(plan->host_mu);
+    for (int i = 0; i < 4; ++i) {
+        if (plan->ws[i]) cudaFree(plan->ws[i]);
+        plan->ws[i] = nullptr; plan->ws_cap[i] = 0;
+    }
+    for (int k = 0; k < b200aa_plan::kPipe; ++k)
+        for (int j = 0; j < 3; ++j) {
+            if (plan->pipe_ws[k][j]) cudaFree(plan->pipe_ws[k][j]);
+            plan->pipe_ws[k][j] = nullptr; plan->pipe_cap[k][j] = 0;
+        }
+    return B200AA_OK;
 }
 
 // a plan's tables live on the device that was current when it was created
@@ -648,7 +691,7 @@ static int launch_generic(const b200aa_plan *pl, StParams &p, int64_t rows_max, 
     if (p.n_items == 0) return B200AA_OK;
     if (big) {
         auto kern = st_generic_kernel<MODE, true>;
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         const int64_t grid = std::min<int64_t>(p.n_items, int64_t(pl->sm_count) * 2);
         p.scratch_stride = generic_big_bytes(G, p.Nc, p.Kp);
         void *scratch = nullptr;
@@ -662,7 +705,7 @@ static int launch_generic(const b200aa_plan *pl, StParams &p, int64_t rows_max, 
         return B200AA_OK;
     }
     auto kern = st_generic_kernel<MODE, false>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));   // constant: no race between launching threads
     int occ = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
     occ = std::max(1, occ);
@@ -696,14 +739,21 @@ extern "C" int b200aa_st_features(const b200aa_plan *plan, const void *d_sig, in
     p.t_stride = t_stride; p.deltas = deltas ? 1 : 0; p.n_out = deltas ? 68 : 34; p.mode = kModeFeatures;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (use_pair(pl)) {
-        unsigned int *ctr = pl->d_counters + (pl->next_counter.fetch_add(1u, std::memory_order_relaxed) % kCounterRing);
+        unsigned slot = 0;
+        unsigned int *ctr = nullptr;
+        if ((rc = slot_acquire(pl, st, &slot, &ctr)) != B200AA_OK) return rc;
         rc = pair_launch_features(pl->pair, p, pl->sm_count, T, ctr, g_pair_dump, st);
-        if (rc == B200AA_OK) { g_launches.fetch_add(1, std::memory_order_relaxed); return rc; }
+        const int rc2 = slot_done(pl, st, slot);
+        if (rc == B200AA_OK) { g_launches.fetch_add(1, std::memory_order_relaxed); return rc2; }
         if (rc != B200AA_ERR_UNSUPPORTED) return rc == B200AA_ERR_CUDA ? cuda_fail(cudaGetLastError(), "pair kernel") : rc;
     }
     if (use_fast(pl)) {
-        rc = fast_launch_features(pl->fast_kind, pl->fast, p, pl->sm_count, T, st);
-        if (rc == B200AA_OK) { g_launches.fetch_add(1, std::memory_order_relaxed); return rc; }
+        unsigned slot = 0;
+        unsigned int *ctr = nullptr;
+        if ((rc = slot_acquire(pl, st, &slot, &ctr)) != B200AA_OK) return rc;
+        rc = fast_launch_features(pl->fast_kind, pl->fast, p, pl->sm_count, T, ctr, st);
+        const int rc2 = slot_done(pl, st, slot);
+        if (rc == B200AA_OK) { g_launches.fetch_add(1, std::memory_order_relaxed); return rc2; }
         if (rc != B200AA_ERR_UNSUPPORTED) return rc == B200AA_ERR_CUDA ? cuda_fail(cudaGetLastError(), "fast kernel") : rc;
     }
     return launch_generic<kModeFeatures>(pl, p, T, st);
@@ -731,8 +781,13 @@ extern "C" int b200aa_spectrogram(const b200aa_plan *plan, const void *d_sig, in
     p.origin = w; p.row0 = 0; p.rows_total = R; p.rows_launch = R;
     p.rows_valid = std::min<int64_t>(R, b200aa_host::range_len(w, n_samples - w + 1, s));   // :415
     if (pl->fast_kind && !pl->force_generic && pl->prefer != 0) {
-        rc = fast_launch_rows(pl->fast_kind, kModeSpectrogram, pl->fast, p, pl->sm_count, static_cast<cudaStream_t>(stream));
-        if (rc == B200AA_OK) { g_launches.fetch_add(1, std::memory_order_relaxed); return rc; }
+        cudaStream_t st_ = static_cast<cudaStream_t>(stream);
+        unsigned slot = 0;
+        unsigned int *ctr = nullptr;
+        if ((rc = slot_acquire(pl, st_, &slot, &ctr)) != B200AA_OK) return rc;
+        rc = fast_launch_rows(pl->fast_kind, kModeSpectrogram, pl->fast, p, pl->sm_count, ctr, st_);
+        const int rc2 = slot_done(pl, st_, slot);
+        if (rc == B200AA_OK) { g_launches.fetch_add(1, std::memory_order_relaxed); return rc2; }
         if (rc != B200AA_ERR_UNSUPPORTED) return rc == B200AA_ERR_CUDA ? cuda_fail(cudaGetLastError(), "fast kernel") : rc;
     }
     return launch_generic<kModeSpectrogram>(pl, p, R, static_cast<cudaStream_t>(stream));
@@ -766,7 +821,11 @@ extern "C" int b200aa_chromagram(const b200aa_plan *plan, const void *d_sig, int
     p.origin = w; p.row0 = 0; p.rows_total = R; p.rows_launch = R; p.rows_valid = n_full;
     rc = B200AA_ERR_UNSUPPORTED;
     if (pl->fast_kind && !pl->force_generic && pl->prefer != 0) {
-        rc = fast_launch_rows(pl->fast_kind, kModeChromagram, pl->fast, p, pl->sm_count, st);
+        unsigned slot = 0;
+        unsigned int *ctr = nullptr;
+        if ((rc = slot_acquire(pl, st, &slot, &ctr)) != B200AA_OK) return rc;
+        rc = fast_launch_rows(pl->fast_kind, kModeChromagram, pl->fast, p, pl->sm_count, ctr, st);
+        if (slot_done(pl, st, slot) != B200AA_OK) return B200AA_ERR_CUDA;
         if (rc == B200AA_OK) g_launches.fetch_add(1, std::memory_order_relaxed);
         else if (rc != B200AA_ERR_UNSUPPORTED) return rc == B200AA_ERR_CUDA ? cuda_fail(cudaGetLastError(), "fast kernel") : rc;
     }

@@ -471,20 +471,15 @@ __device__ __forceinline__ void stage_run_smem(const short *raw8, bool has_pred,
 // ----------------------------------------------------------------------------------------------
 // kernel
 // ----------------------------------------------------------------------------------------------
-constexpr unsigned int kCounterRing = 1024;   // launches that may be in flight at once on different streams
-
 struct FastTables {
     float2 *d_tw = nullptr;      // [R][R]   W_Nc^(k1*n2) stored [k1][n2]
     float2 *d_twp = nullptr;     // [Nc/2+1] W_N^k
-    unsigned int *d_counters = nullptr;   // ring of work counters (one per in-flight launch; zeroed in-stream before use)
-    mutable std::atomic<unsigned int> next_counter{0};
     int R = 0;
     void release()
     {
         if (d_tw) cudaFree(d_tw);
         if (d_twp) cudaFree(d_twp);
-        if (d_counters) cudaFree(d_counters);
-        d_tw = d_twp = nullptr; d_counters = nullptr;
+        d_tw = d_twp = nullptr;
     }
 };
 
@@ -902,7 +897,6 @@ inline int fast_plan_init(int fs, int window, int step, const std::vector<int> &
     if (cudaMalloc(&ft->d_twp, twp.size() * sizeof(float2)) != cudaSuccess) return B200AA_ERR_CUDA;
     if (cudaMemcpy(ft->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) return B200AA_ERR_CUDA;
     if (cudaMemcpy(ft->d_twp, twp.data(), twp.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) return B200AA_ERR_CUDA;
-    if (cudaMalloc(&ft->d_counters, kCounterRing * sizeof(unsigned int)) != cudaSuccess) return B200AA_ERR_CUDA;
     ft->R = R1 * 100 + R2;
     *kind = ft->R;
     return B200AA_OK;
@@ -910,13 +904,14 @@ inline int fast_plan_init(int fs, int window, int step, const std::vector<int> &
 
 #ifndef B200AA_LAYOUT_ONLY     // tests/smem_budget_host.cu includes this header for the layout arithmetic only
 template <int R1, int R2, int G, bool EVEN, bool RUNS, int MODE>
-inline int fast_launch_t(const FastTables &ft, StParams p, int sm_count, int64_t T, cudaStream_t st)
+inline int fast_launch_t(const FastTables &ft, StParams p, int sm_count, int64_t T, unsigned int *ctr, cudaStream_t st)
 {
     constexpr int NT = fast_threads(G);
     const size_t smem = fast_smem_bytes<R1, R2, G>(p.step, p.bl.words, RUNS);
     if (smem > 110u * 1024u) return B200AA_ERR_UNSUPPORTED;      // very large hop: leave it to the generic kernel
     auto kern = st_fast_kernel<R1, R2, G, EVEN, RUNS, MODE>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200AA_ERR_CUDA;
+    // always the same value (the launcher's cap), so concurrent launches of one instantiation cannot undercut each other
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) != cudaSuccess) return B200AA_ERR_CUDA;
     int occ = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem) != cudaSuccess) return B200AA_ERR_CUDA;
     occ = occ < 1 ? 1 : occ;
@@ -942,7 +937,6 @@ inline int fast_launch_t(const FastTables &ft, StParams p, int sm_count, int64_t
     if (getenv("B200AA_DEBUG"))
         fprintf(stderr, "[b200aa] fast kernel %dx%d G=%d runs=%d mode=%d: smem %zu B, %d CTAs/SM, grid %lld, %lld items of %lld frames\n",
                 R1, R2, G, int(RUNS), MODE, smem, occ, (long long)grid, (long long)p.n_items, (long long)seg);
-    unsigned int *ctr = ft.d_counters + (ft.next_counter.fetch_add(1u, std::memory_order_relaxed) % kCounterRing);
     if (cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st) != cudaSuccess) return B200AA_ERR_CUDA;
     kern<<<(unsigned)grid, NT, smem, st>>>(p, ft.d_tw, ft.d_twp, ctr);
     return cudaPeekAtLastError() == cudaSuccess ? B200AA_OK : B200AA_ERR_CUDA;    // the caller fetches (and clears) the text
@@ -950,43 +944,43 @@ inline int fast_launch_t(const FastTables &ft, StParams p, int sm_count, int64_t
 
 // run staging needs whole 8-sample runs per frame, per entropy block (window % 80 == 0) and per hop
 template <int R1, int R2, int MODE>
-inline int fast_launch_shape(const FastTables &ft, const StParams &p, int sm_count, int64_t T, cudaStream_t st)
+inline int fast_launch_shape(const FastTables &ft, const StParams &p, int sm_count, int64_t T, unsigned int *ctr, cudaStream_t st)
 {
     constexpr int G = B200AA_FAST_G;
     constexpr int N = 2 * R1 * R2;
     const bool even = (p.step % 2) == 0 && (p.origin % 2) == 0;
     if (N % 80 == 0) {
         const bool runs = (p.step % 8) == 0 && (p.clip_stride % 8) == 0 && (p.origin % 8) == 0;
-        if (runs) return fast_launch_t<R1, R2, G, true, N % 80 == 0, MODE>(ft, p, sm_count, T, st);
+        if (runs) return fast_launch_t<R1, R2, G, true, N % 80 == 0, MODE>(ft, p, sm_count, T, ctr, st);
     }
-    return even ? fast_launch_t<R1, R2, G, true, false, MODE>(ft, p, sm_count, T, st)
-                : fast_launch_t<R1, R2, G, false, false, MODE>(ft, p, sm_count, T, st);
+    return even ? fast_launch_t<R1, R2, G, true, false, MODE>(ft, p, sm_count, T, ctr, st)
+                : fast_launch_t<R1, R2, G, false, false, MODE>(ft, p, sm_count, T, ctr, st);
 }
 
 template <int MODE>
-inline int fast_launch_mode(int kind, const FastTables &ft, const StParams &p, int sm_count, int64_t T, cudaStream_t st)
+inline int fast_launch_mode(int kind, const FastTables &ft, const StParams &p, int sm_count, int64_t T, unsigned int *ctr, cudaStream_t st)
 {
     switch (kind) {
-    case 2020: return fast_launch_shape<20, 20, MODE>(ft, p, sm_count, T, st);
-    case 2121: return fast_launch_shape<21, 21, MODE>(ft, p, sm_count, T, st);
-    case 2010: return fast_launch_shape<20, 10, MODE>(ft, p, sm_count, T, st);
-    case 2012: return fast_launch_shape<20, 12, MODE>(ft, p, sm_count, T, st);
-    case 2015: return fast_launch_shape<20, 15, MODE>(ft, p, sm_count, T, st);
-    case 1610: return fast_launch_shape<16, 10, MODE>(ft, p, sm_count, T, st);
-    case 2016: return fast_launch_shape<20, 16, MODE>(ft, p, sm_count, T, st);
+    case 2020: return fast_launch_shape<20, 20, MODE>(ft, p, sm_count, T, ctr, st);
+    case 2121: return fast_launch_shape<21, 21, MODE>(ft, p, sm_count, T, ctr, st);
+    case 2010: return fast_launch_shape<20, 10, MODE>(ft, p, sm_count, T, ctr, st);
+    case 2012: return fast_launch_shape<20, 12, MODE>(ft, p, sm_count, T, ctr, st);
+    case 2015: return fast_launch_shape<20, 15, MODE>(ft, p, sm_count, T, ctr, st);
+    case 1610: return fast_launch_shape<16, 10, MODE>(ft, p, sm_count, T, ctr, st);
+    case 2016: return fast_launch_shape<20, 16, MODE>(ft, p, sm_count, T, ctr, st);
     default: return B200AA_ERR_UNSUPPORTED;
     }
 }
 
-inline int fast_launch_features(int kind, const FastTables &ft, const StParams &p, int sm_count, int64_t T, cudaStream_t st)
+inline int fast_launch_features(int kind, const FastTables &ft, const StParams &p, int sm_count, int64_t T, unsigned int *ctr, cudaStream_t st)
 {
-    return fast_launch_mode<kModeFeatures>(kind, ft, p, sm_count, T, st);
+    return fast_launch_mode<kModeFeatures>(kind, ft, p, sm_count, T, ctr, st);
 }
 // spectrogram / chromagram rows of full-length frames (p.origin, p.rows_* filled by the caller)
-inline int fast_launch_rows(int kind, int mode, const FastTables &ft, const StParams &p, int sm_count, cudaStream_t st)
+inline int fast_launch_rows(int kind, int mode, const FastTables &ft, const StParams &p, int sm_count, unsigned int *ctr, cudaStream_t st)
 {
-    if (mode == kModeSpectrogram) return fast_launch_mode<kModeSpectrogram>(kind, ft, p, sm_count, p.rows_launch, st);
-    return fast_launch_mode<kModeChromagram>(kind, ft, p, sm_count, p.rows_launch, st);
+    if (mode == kModeSpectrogram) return fast_launch_mode<kModeSpectrogram>(kind, ft, p, sm_count, p.rows_launch, ctr, st);
+    return fast_launch_mode<kModeChromagram>(kind, ft, p, sm_count, p.rows_launch, ctr, st);
 }
 #endif  // B200AA_LAYOUT_ONLY
 
