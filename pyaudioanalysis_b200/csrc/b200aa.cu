@@ -1,6 +1,7 @@
 // libb200aa.so -- C ABI (include/b200aa.h) over the sm_100a kernels.
 // Build: see pyaudioanalysis_b200/build.py (nvcc -gencode arch=compute_100a,code=sm_100a).
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX 3: ranges around the entry points (visible in nsys / ncu timelines)
 
 #include <algorithm>
 #include <atomic>
@@ -44,6 +45,11 @@ static int cuda_fail(cudaError_t e, const char *what)
         cudaError_t e_ = cudaGetLastError();                         \
         if (e_ != cudaSuccess) return cuda_fail(e_, name);           \
     } while (0)
+
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 extern "C" int b200aa_abi_version(void) { return B200AA_ABI_VERSION; }
 extern "C" int64_t b200aa_launch_count(void) { return g_launches.load(); }
@@ -428,7 +434,27 @@ __global__ void __launch_bounds__(256) stats_accum_kernel(const void *sig, int64
         if (al) {
             const int4 *v = reinterpret_cast<const int4 *>(x + s0);
             const int64_t nv = (s1 - s0) / 8;
-            for (int64_t j = threadIdx.x; j < nv; j += blockDim.x) {
+            // four 16-byte loads in flight per thread (the kernel is a pure HBM stream: memory-level parallelism is all it needs)
+            int64_t j = threadIdx.x;
+            for (; j + 3 * int64_t(blockDim.x) < nv; j += 4 * int64_t(blockDim.x)) {
+                int4 q[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) q[t] = __ldg(v + j + t * int64_t(blockDim.x));
+                int acc = 0;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int w4[4] = {q[t].x, q[t].y, q[t].z, q[t].w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int a0 = (short)(w4[u] & 0xffff), a1 = w4[u] >> 16;
+                        acc += a0 + a1;
+                        mn = min(mn, min(a0, a1));
+                        mx = max(mx, max(a0, a1));
+                    }
+                }
+                isum += acc;
+            }
+            for (; j < nv; j += blockDim.x) {
                 int acc = 0;
                 const int4 q = __ldg(v + j);
                 const int w4[4] = {q.x, q.y, q.z, q.w};
@@ -533,6 +559,7 @@ __global__ void stats_finish_kernel(b200aa_clip_norm *nm, int64_t n, int64_t n_s
 extern "C" int b200aa_clip_stats(const void *d_sig, int dtype, int64_t n_clips, int64_t n_samples,
                                  int64_t clip_stride, const int64_t *d_len, b200aa_clip_norm *d_norm, void *stream)
 {
+    NvtxRange nvtx_("b200aa_clip_stats");
     if (!d_sig || !d_norm || n_clips < 0 || n_samples < 0 || (dtype != 0 && dtype != 1)) return B200AA_ERR_INVALID;
     if (n_clips == 0) return B200AA_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -603,6 +630,7 @@ __global__ void __launch_bounds__(256) mid_pool_kernel(const float *st, int64_t 
 extern "C" int b200aa_mid_pool(const float *d_st, int64_t n_clips, int n_feats, int64_t n_frames, int64_t t_stride,
                                int ratio, int step_ratio, float *d_mid, void *stream)
 {
+    NvtxRange nvtx_("b200aa_mid_pool");
     if (!d_st || !d_mid || n_clips < 0 || n_feats < 1 || n_frames < 1 || ratio < 1 || step_ratio < 1 || t_stride < n_frames)
         return B200AA_ERR_INVALID;
     const int64_t M = b200aa_mid_windows(n_frames, step_ratio);
@@ -719,6 +747,7 @@ extern "C" int b200aa_st_features(const b200aa_plan *plan, const void *d_sig, in
                                   int64_t n_samples, int64_t clip_stride, const int64_t *d_len,
                                   const b200aa_clip_norm *d_norm, int deltas, float *d_out, int64_t t_stride, void *stream)
 {
+    NvtxRange nvtx_("b200aa_st_features");
     if (!plan || !d_sig || !d_norm || !d_out || n_clips < 0 || (dtype != 0 && dtype != 1) || clip_stride < n_samples)
         return B200AA_ERR_INVALID;
     b200aa_plan *pl = const_cast<b200aa_plan *>(plan);
@@ -763,6 +792,7 @@ extern "C" int b200aa_spectrogram(const b200aa_plan *plan, const void *d_sig, in
                                   int64_t n_samples, int64_t clip_stride, const b200aa_clip_norm *d_norm,
                                   float *d_out, void *stream)
 {
+    NvtxRange nvtx_("b200aa_spectrogram");
     if (!plan || !d_sig || !d_norm || !d_out || n_clips < 0 || (dtype != 0 && dtype != 1) || clip_stride < n_samples)
         return B200AA_ERR_INVALID;
     b200aa_plan *pl = const_cast<b200aa_plan *>(plan);
@@ -797,6 +827,7 @@ extern "C" int b200aa_chromagram(const b200aa_plan *plan, const void *d_sig, int
                                  int64_t n_samples, int64_t clip_stride, const b200aa_clip_norm *d_norm,
                                  float *d_out, void *stream)
 {
+    NvtxRange nvtx_("b200aa_chromagram");
     if (!plan || !d_sig || !d_norm || !d_out || n_clips < 0 || (dtype != 0 && dtype != 1) || clip_stride < n_samples)
         return B200AA_ERR_INVALID;
     b200aa_plan *pl = const_cast<b200aa_plan *>(plan);
@@ -952,6 +983,7 @@ static int st_features_host_pipelined(b200aa_plan *pl, const void *h_sig, int dt
 extern "C" int b200aa_st_features_host(const b200aa_plan *plan, const void *h_sig, int dtype, int64_t n_clips,
                                        int64_t n_samples, int deltas, float *h_out)
 {
+    NvtxRange nvtx_("b200aa_st_features_host");
     if (!plan || !h_sig || !h_out || n_clips < 1 || (dtype != 0 && dtype != 1)) return B200AA_ERR_INVALID;
     if (plan->tables_status == B200AA_ERR_MEL_RANGE) return B200AA_ERR_MEL_RANGE;
     const int64_t T = b200aa_host::num_frames(n_samples, plan->window, plan->step);
@@ -1012,6 +1044,7 @@ extern "C" int b200aa_chromagram_host(const b200aa_plan *plan, const void *h_sig
 extern "C" int b200aa_mid_features_host(const b200aa_plan *plan, const void *h_sig, int dtype, int64_t n_samples,
                                         int ratio, int step_ratio, float *h_mid, float *h_st)
 {
+    NvtxRange nvtx_("b200aa_mid_features_host");
     if (!plan || !h_sig || !h_mid || ratio < 1 || step_ratio < 1 || (dtype != 0 && dtype != 1)) return B200AA_ERR_INVALID;
     if (plan->tables_status == B200AA_ERR_MEL_RANGE) return B200AA_ERR_MEL_RANGE;
     const int64_t T = b200aa_host::num_frames(n_samples, plan->window, plan->step);
