@@ -330,19 +330,19 @@ __device__ __forceinline__ void td_frame(const float (&u)[R], float cm, const b2
                 if (!FULL && r == Td::ROW0) lk += int((cQ >> Td::LANE0) & 1u);
             }
             // ---- energy of the normalised samples into the row's block(s)
+            // (fused multiply-adds, predicated: bit-identical to td_pair below, whichever of the two handles a frame)
             const float y = fmaf(nm.a, d, nm.bp);
-            float q = y * y;
-            if (r == Td::ROW0 && Td::LANE0 > 0) q = lane >= Td::LANE0 ? q : 0.f;
+            const bool live = !(r == Td::ROW0 && Td::LANE0 > 0) || lane >= Td::LANE0;
             const int b0 = (n0 / Lt) < 10 ? (n0 / Lt) : 10;
             const int end = b0 < 10 ? (b0 + 1) * Lt : N;
             const int thr = end - n0;                     // samples of this row that still belong to block b0
             const int i0 = b0 - Td::EB, i1 = (b0 + 1 < 10 ? b0 + 1 : 10) - Td::EB;
             if (thr >= 32) {
-                if (i0 >= 0 && i0 < Td::NE) e[i0] += q;
+                if (i0 >= 0 && i0 < Td::NE) { if (live) e[i0] = fmaf(y, y, e[i0]); }
             } else {
                 const bool first = lane < thr;
-                if (i0 >= 0 && i0 < Td::NE) e[i0] += first ? q : 0.f;
-                if (i1 >= 0 && i1 < Td::NE) e[i1] += first ? 0.f : q;
+                if (i0 >= 0 && i0 < Td::NE) { if (live && first) e[i0] = fmaf(y, y, e[i0]); }
+                if (i1 >= 0 && i1 < Td::NE) { if (live && !first) e[i1] = fmaf(y, y, e[i1]); }
             }
         }
         prevP = P; prevQ = Q;
@@ -350,6 +350,57 @@ __device__ __forceinline__ void td_frame(const float (&u)[R], float cm, const b2
     // one-sided counting saw every change once; |s_n - s_(n-1)| is 2 for a sign change without a zero in between
     flips = TWO ? fl : 2 * fl;
     link = TWO ? lk : 2 * lk;
+}
+
+// The same accumulation for BOTH frames of a pair at once (they cover the same rows): u[r] = (sample of a, sample of b),
+// e2[i] = (block sum of a, block sum of b) -- the arithmetic runs in FP32x2 instructions, only the sign masks stay per frame.
+template <int R, bool FULL, bool TWO>
+__device__ __forceinline__ void td_pair(const float2 (&u)[R], float cm, const b200aa_clip_norm &nm, int lane,
+                                        float2 *e2 /* [NE] */, int &flips_a, int &link_a, int &flips_b, int &link_b)
+{
+    using S = PairShape<R>;
+    using Td = TdShape<R, FULL>;
+    constexpr int N = S::N, Lt = S::Lt;
+    unsigned pPa = 0u, pQa = 0u, pPb = 0u, pQb = 0u;
+    int fa = 0, la = 0, fb = 0, lb = 0;
+    const float2 ncm = make_float2(-cm, -cm), a2 = make_float2(nm.a, nm.a), bp2 = make_float2(nm.bp, nm.bp);
+#pragma unroll
+    for (int r = Td::ZROW0; r < R; ++r) {
+        const float2 d = __fadd2_rn(u[r], ncm);
+        const unsigned Pa = __ballot_sync(0xffffffffu, d.x > nm.lo), Pb = __ballot_sync(0xffffffffu, d.y > nm.lo);
+        unsigned Qa = 0u, Qb = 0u;
+        if (TWO) { Qa = __ballot_sync(0xffffffffu, d.x < nm.hi); Qb = __ballot_sync(0xffffffffu, d.y < nm.hi); }
+        if (FULL && r == 0) { pPa = (Pa & 1u) << 31; pQa = (Qa & 1u) << 31; pPb = (Pb & 1u) << 31; pQb = (Qb & 1u) << 31; }
+        if (r >= Td::ROW0) {
+            const int n0 = 32 * r;
+            const int nstart = FULL ? 1 : Td::NFIRST;
+            const unsigned valid = n0 >= nstart ? 0xffffffffu : (n0 + 32 <= nstart ? 0u : (0xffffffffu << (nstart - n0)));
+            const unsigned cPa = (Pa ^ __funnelshift_l(pPa, Pa, 1)) & valid, cPb = (Pb ^ __funnelshift_l(pPb, Pb, 1)) & valid;
+            fa += __popc(cPa); fb += __popc(cPb);
+            if (!FULL && r == Td::ROW0) { la += int((cPa >> Td::LANE0) & 1u); lb += int((cPb >> Td::LANE0) & 1u); }
+            if (TWO) {
+                const unsigned cQa = (Qa ^ __funnelshift_l(pQa, Qa, 1)) & valid, cQb = (Qb ^ __funnelshift_l(pQb, Qb, 1)) & valid;
+                fa += __popc(cQa); fb += __popc(cQb);
+                if (!FULL && r == Td::ROW0) { la += int((cQa >> Td::LANE0) & 1u); lb += int((cQb >> Td::LANE0) & 1u); }
+            }
+            const float2 y = __ffma2_rn(a2, d, bp2);
+            const bool live = !(r == Td::ROW0 && Td::LANE0 > 0) || lane >= Td::LANE0;
+            const int b0 = (n0 / Lt) < 10 ? (n0 / Lt) : 10;
+            const int end = b0 < 10 ? (b0 + 1) * Lt : N;
+            const int thr = end - n0;
+            const int i0 = b0 - Td::EB, i1 = (b0 + 1 < 10 ? b0 + 1 : 10) - Td::EB;
+            if (thr >= 32) {
+                if (i0 >= 0 && i0 < Td::NE) { if (live) e2[i0] = __ffma2_rn(y, y, e2[i0]); }
+            } else {
+                const bool first = lane < thr;
+                if (i0 >= 0 && i0 < Td::NE) { if (live && first) e2[i0] = __ffma2_rn(y, y, e2[i0]); }
+                if (i1 >= 0 && i1 < Td::NE) { if (live && !first) e2[i1] = __ffma2_rn(y, y, e2[i1]); }
+            }
+        }
+        pPa = Pa; pQa = Qa; pPb = Pb; pQb = Qb;
+    }
+    flips_a = TWO ? fa : 2 * fa; link_a = TWO ? la : 2 * la;
+    flips_b = TWO ? fb : 2 * fb; link_b = TWO ? lb : 2 * lb;
 }
 
 // power of two s with s * rms(x - x0) ~ 1 (E = sum y^2 of the frame, y = a (x - mean)); its inverse
@@ -444,20 +495,20 @@ __global__ void __launch_bounds__(32 * pair_warps<R>(), kPairMinBlocks) st_pair_
             const bool store = q >= q0;
             const int ta = 2 * q;
             const bool bvalid = ta + 1 < T;
-            float ua[R], ub[R];
-            unsigned int wa[R], wb[R];
-            load_pair(q, wa, wb);
-            if (is16) {
+            float2 uab[R];                      // (sample of a, sample of b) per row: FP32x2 operands
+            {
+                unsigned int wa[R], wb[R];
+                load_pair(q, wa, wb);
+                if (is16) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    ua[r] = __int_as_float(0x4B000000 | (int(wa[r]) ^ 0x8000));
-                    ub[r] = __int_as_float(0x4B000000 | (int(wb[r]) ^ 0x8000));
+                    for (int r = 0; r < R; ++r)
+                        uab[r] = make_float2(__int_as_float(0x4B000000 | (int(wa[r]) ^ 0x8000)), __int_as_float(0x4B000000 | (int(wb[r]) ^ 0x8000)));
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) uab[r] = make_float2(__int_as_float(wa[r]), __int_as_float(wb[r]));
                 }
-            } else {
-#pragma unroll
-                for (int r = 0; r < R; ++r) { ua[r] = __int_as_float(wa[r]); ub[r] = __int_as_float(wb[r]); }
             }
-            const float u0a = __shfl_sync(FULLM, ua[0], 0), u0b = __shfl_sync(FULLM, ub[0], 0);   // first samples
+            const float u0a = __shfl_sync(FULLM, uab[0].x, 0), u0b = __shfl_sync(FULLM, uab[0].y, 0);   // first samples
             const int ra = store ? 1 + tile_n : 8, rb = store ? 2 + tile_n : 0;     // feature rows (a halo's b is "previous")
             float *const fva = wm.fv + ra * kFvStride, *const fvb = wm.fv + rb * kFvStride;
 
@@ -468,12 +519,15 @@ __global__ void __launch_bounds__(32 * pair_warps<R>(), kPairMinBlocks) st_pair_
                 constexpr int NEF = TdShape<R, true>::NE, NREST = TdShape<R, true>::NREST;
                 if constexpr (SHARED) { if (!a_full) {
                     // steady state: the second halves of a and b are new
+                    float2 e2[5];
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) e2[i] = make_float2(0.f, 0.f);
+                    int fa_, la_, fb_, lb_;
+                    if (two_sided) td_pair<R, false, true>(uab, cmv, nm, lane, e2, fa_, la_, fb_, lb_);
+                    else td_pair<R, false, false>(uab, cmv, nm, lane, e2, fa_, la_, fb_, lb_);
                     float ev[10];
 #pragma unroll
-                    for (int i = 0; i < 10; ++i) ev[i] = 0.f;
-                    int fa_, la_, fb_, lb_;
-                    if (two_sided) { td_frame<R, false, true>(ua, cmv, nm, lane, ev, fa_, la_); td_frame<R, false, true>(ub, cmv, nm, lane, ev + 5, fb_, lb_); }
-                    else { td_frame<R, false, false>(ua, cmv, nm, lane, ev, fa_, la_); td_frame<R, false, false>(ub, cmv, nm, lane, ev + 5, fb_, lb_); }
+                    for (int i = 0; i < 5; ++i) { ev[i] = e2[i].x; ev[5 + i] = e2[i].y; }
                     if (lane < 5) wm.blk[lane] = wm.blk[10 + lane];                 // previous b's second half = a's first half
                     MultiReduce<10>::run(ev, lane);
                     __syncwarp();
@@ -483,6 +537,9 @@ __global__ void __launch_bounds__(32 * pair_warps<R>(), kPairMinBlocks) st_pair_
                     zprev = fb_ - lb_;
                 } else {
                     // first step of a run: all of a, the second half of b
+                    float ua[R], ub[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) { ua[r] = uab[r].x; ub[r] = uab[r].y; }
                     float ev[NEF + 5];
 #pragma unroll
                     for (int i = 0; i < NEF + 5; ++i) ev[i] = 0.f;
@@ -505,12 +562,15 @@ __global__ void __launch_bounds__(32 * pair_warps<R>(), kPairMinBlocks) st_pair_
                     zprev = fb_ - lb_;
                 } } else {
                     // independent frames (any hop)
+                    float2 e2[NEF];
+#pragma unroll
+                    for (int i = 0; i < NEF; ++i) e2[i] = make_float2(0.f, 0.f);
+                    int la_, lb_;
+                    if (two_sided) td_pair<R, true, true>(uab, cmv, nm, lane, e2, fl_a, la_, fl_b, lb_);
+                    else td_pair<R, true, false>(uab, cmv, nm, lane, e2, fl_a, la_, fl_b, lb_);
                     float ev[2 * NEF];
 #pragma unroll
-                    for (int i = 0; i < 2 * NEF; ++i) ev[i] = 0.f;
-                    int la_, lb_;
-                    if (two_sided) { td_frame<R, true, true>(ua, cmv, nm, lane, ev, fl_a, la_); td_frame<R, true, true>(ub, cmv, nm, lane, ev + NEF, fl_b, lb_); }
-                    else { td_frame<R, true, false>(ua, cmv, nm, lane, ev, fl_a, la_); td_frame<R, true, false>(ub, cmv, nm, lane, ev + NEF, fl_b, lb_); }
+                    for (int i = 0; i < NEF; ++i) { ev[i] = e2[i].x; ev[NEF + i] = e2[i].y; }
                     MultiReduce<2 * NEF>::run(ev, lane);
                     __syncwarp();
                     {
@@ -551,11 +611,11 @@ __global__ void __launch_bounds__(32 * pair_warps<R>(), kPairMinBlocks) st_pair_
             bool a_flat, b_flat;        // every sample equals the frame's first one: the spectrum is exactly zero beyond DC
             {
                 float2 z[R];
-                const float oa = -u0a * sa, ob = -u0b * sb;
+                const float2 s2 = make_float2(sa, sb), o2 = make_float2(-u0a * sa, -u0b * sb);
                 float2 zz = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    z[r] = make_float2(fmaf(ua[r], sa, oa), fmaf(ub[r], sb, ob));
+                    z[r] = __ffma2_rn(uab[r], s2, o2);
                     zz = __ffma2_rn(z[r], z[r], zz);
                 }
                 // A constant frame must come out as exact zeros (the reference's float64 spectrum is ~1e-17 there, and
@@ -600,9 +660,10 @@ __global__ void __launch_bounds__(32 * pair_warps<R>(), kPairMinBlocks) st_pair_
                     xa[j] = 0.f; xb[j] = 0.f;
                     if (j < JK && k < K) {
                         const float2 zk = wm.tz[k], pk = wm.tz[N - k];
-                        const float sx_ = zk.x + pk.x, sy_ = zk.y - pk.y, dx_ = zk.x - pk.x, dy_ = zk.y + pk.y;
-                        xa[j] = fsqrt_fast(fmaf(sx_, sx_, sy_ * sy_)) * fa;
-                        xb[j] = fsqrt_fast(fmaf(dx_, dx_, dy_ * dy_)) * fb;
+                        // Z + conj P = (zx + px, zy - py), Z - conj P = (zx - px, zy + py): one packed sum, one packed difference
+                        const float2 sm_ = f2add(zk, pk), df_ = f2sub(zk, pk);
+                        xa[j] = fsqrt_fast(fmaf(sm_.x, sm_.x, df_.y * df_.y)) * fa;
+                        xb[j] = fsqrt_fast(fmaf(df_.x, df_.x, sm_.y * sm_.y)) * fb;
                     }
                 }
                 if (lane == 0) {
