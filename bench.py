@@ -6,9 +6,10 @@
 Workload (config.workload): BASELINE.json configs[1] -- 1000 synthetic 16 kHz mono int16 10 s clips per
 GPU, window/step 50/25 ms, full 68-row short-term feature matrix.  One "step" = the whole hot path
 over the batch: clip statistics (kernel 0) + fused short-term features (kernel 1); for N > 1 every
-rank's feature kernel stores its [clips, 68, T] block straight into rank 0's peer-mapped gather buffer
-(NVLink, b200aa_peer_buffer_*), i.e. the gather is part of the step (`scaling_detail` also gives the
-step without any gather and with a plain NCCL gather).
+rank's [clips, 68, T] block is pushed by the copy engines into rank 0's peer-mapped gather buffer
+(NVLink, b200aa_peer_buffer_* / b200aa_peer_copy) under the next step's kernels, all pushes inside the timed
+region (`scaling_detail` also gives the step without any gather, with a plain NCCL gather, and with the
+gather fused into the kernel's stores).
 Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the same metric
 through the C ABI's host entry point b200aa_st_features_host (pinned host clips in, pinned host features
 out, copies inside the timed region); `roofline` = algorithmic bytes / kernel time of the fused kernel
@@ -296,34 +297,58 @@ def run_ours(args, rank, world, local_rank):
     plan = _lib.get_plan(FS, WINDOW, STEP, local_rank)
     T = FRAMES_PER_CLIP
     local_out = torch.empty((B, 68, T), dtype=torch.float32, device=dev)
-    # N > 1: rank 0 owns a [world*B, 68, T] buffer that every rank maps over NVLink; a rank's kernel writes its block
-    # straight into it (double-buffered per step parity so that step i+1 never overwrites what the root may still read)
+    # N > 1: rank 0 owns a [world*B, 68, T] buffer that every rank maps over NVLink.  Default gather ("ce"): a rank's
+    # kernels write a local block (double-buffered) and the copy engines push it into rank 0's buffer on a second
+    # stream, under the kernels of the next step; all pushes complete inside the timed region.  "p2p_store": the kernel
+    # stores straight into the mapped buffer; "nccl": torch.distributed.gather; "none": no gather.
     gathers = [PeerGather(world * B, 68, T, dst=0) for _ in range(2)] if world > 1 else None
     nccl_dst = [torch.empty((world, B, 68, T), dtype=torch.float32, device=dev)] if (world > 1 and rank == 0) else None
+    local2 = [local_out, torch.empty_like(local_out)] if world > 1 else [local_out]
+    copy_stream = torch.cuda.Stream(dev) if world > 1 else None
 
     ev = lambda: torch.cuda.Event(enable_timing=True)     # noqa: E731
 
     def timed(mode, steps, record_kernel=False):
-        """`steps` passes in gather mode `mode` ('p2p' | 'none' | 'nccl'); returns (ms total max over ranks, kernel ms)."""
+        """`steps` passes in gather mode `mode` ('ce' | 'p2p_store' | 'none' | 'nccl'); returns (ms total max over ranks, kernel ms)."""
         ks, ke = [ev() for _ in range(steps)], [ev() for _ in range(steps)]
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        cur = torch.cuda.current_stream()
+        pushed = [None, None]
         e0, e1 = ev(), ev()
         e0.record()
         for i in range(steps):
             norm = pkg.clip_stats(clips)
-            out = gathers[i % 2].view(rank * B, (rank + 1) * B) if (mode == "p2p" and world > 1) else local_out
+            if mode == "p2p_store" and world > 1:
+                out = gathers[i % 2].view(rank * B, (rank + 1) * B)
+            elif mode == "ce" and world > 1:
+                if rank == 0:
+                    out = gathers[i % 2].view(0, B)                 # the root's own block needs no copy
+                else:
+                    out = local2[i % 2]
+                    if pushed[i % 2] is not None:
+                        cur.wait_event(pushed[i % 2])               # the block's previous push must have left the buffer
+            else:
+                out = local_out
             ks[i].record()
             pkg.feature_extraction_batch(clips, FS, WINDOW, STEP, deltas=True, out=out, norm=norm, plan=plan)
             ke[i].record()
+            if mode == "ce" and world > 1 and rank != 0:
+                copy_stream.wait_event(ke[i])
+                gathers[i % 2].push(out, rank * B, stream=copy_stream)
+                pushed[i % 2] = torch.cuda.Event()
+                pushed[i % 2].record(copy_stream)
             if mode == "nccl" and world > 1:
                 dist.gather(local_out, [nccl_dst[0][r] for r in range(world)] if rank == 0 else None, dst=0)
+        for p_ in pushed:
+            if p_ is not None:
+                cur.wait_event(p_)                                  # every push completes inside the timed region
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
-            dist.barrier()          # all ranks' remote stores have landed before the clock is read
+            dist.barrier()          # all ranks' transfers have landed before the clock is read
         ms = e0.elapsed_time(e1)
         kms = sum(a.elapsed_time(b) for a, b in zip(ks, ke)) / steps
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -331,7 +356,7 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), kms
 
-    main_mode = "p2p" if world > 1 else "none"
+    main_mode = "ce" if world > 1 else "none"
     timed(main_mode, max(3, args.warmup))
     launches0 = L.b200aa_launch_count()
     with ClockSampler(local_rank) as clk:
@@ -351,18 +376,25 @@ def run_ours(args, rank, world, local_rank):
         ms_none, _ = timed("none", args.steps)
         timed("nccl", 3)
         ms_nccl, _ = timed("nccl", args.steps)
+        timed("p2p_store", 3)
+        ms_store, _ = timed("p2p_store", args.steps)
         gather_bytes = (world - 1) * B * 68 * T * 4
-        scaling_detail = {"gather": "fused: every rank's feature kernel stores its block into rank 0's peer-mapped buffer (NVLink)",
-                          "frames_per_s_with_fused_gather": value,
+        scaling_detail = {"gather": "copy-engine push: every rank's finished block goes into rank 0's peer-mapped buffer (NVLink) on a second stream, "
+                                    "under the next step's kernels; all pushes complete inside the timed region",
+                          "frames_per_s_with_gather": value,
                           "frames_per_s_without_gather": frames_per_step / (ms_none / args.steps * 1e-3),
                           "frames_per_s_with_nccl_gather": frames_per_step / (ms_nccl / args.steps * 1e-3),
-                          "ms_per_step": {"fused_gather": ms_per_step, "no_gather": ms_none / args.steps, "nccl_gather": ms_nccl / args.steps},
+                          "frames_per_s_with_gather_fused_into_kernel_stores": frames_per_step / (ms_store / args.steps * 1e-3),
+                          "ms_per_step": {"ce_push_gather": ms_per_step, "no_gather": ms_none / args.steps, "nccl_gather": ms_nccl / args.steps,
+                                          "kernel_store_gather": ms_store / args.steps},
                           "root_ingress_bytes_per_step": gather_bytes,
-                          "root_ingress_GBps_fused": gather_bytes / (ms_per_step * 1e-3) / 1e9,
-                          "limiter": "root NVLink ingress (7 blocks of 108.5 MB per step at N=8 against ~770 GB/s measured per direction)"}
+                          "root_ingress_GBps": gather_bytes / (ms_per_step * 1e-3) / 1e9,
+                          "limiter": "root NVLink ingress: (N-1) blocks of 108.5 MB per step against ~770 GB/s measured per direction "
+                                     "(at N = 8 the gather, not the kernels, sets the step time)"}
         # the gathered tensor on the root holds every rank's block (spot check against the local result)
+        timed("ce", 2)
         if rank == 0:
-            full = gathers[(args.steps - 1) % 2].view(0, world * B)
+            full = gathers[1].view(0, world * B)
             pkg.feature_extraction_batch(clips, FS, WINDOW, STEP, deltas=True, out=local_out, plan=plan)
             torch.cuda.synchronize()
             assert torch.equal(full[:B], local_out), "gather buffer does not hold rank 0's block"

@@ -162,12 +162,15 @@ int b200aa_host_free(void *h_ptr);
 
 /* Peer-mapped gather target (BASELINE configs[4]): the root rank creates one device buffer for the
  * features of ALL clips and exports a 64-byte handle; every other rank of the box opens it (CUDA IPC, NVLink peer
- * mapping) and passes `peer_ptr + its slice offset` as d_out of b200aa_st_features, so the tile stores of the
- * fused kernel land in the root's HBM: the gather needs no collective kernel and no SMs on the root.  Handles
- * travel between the processes by any byte channel (the Python host side uses torch.distributed). */
+ * mapping).  A rank then either pushes its finished block with b200aa_peer_copy (copy engines, asynchronous on a
+ * stream of its own so the transfer rides under the next batch's kernels; no collective kernel, no SM on either
+ * side) or passes `peer_ptr + its slice offset` straight as d_out of b200aa_st_features (the tile stores land in
+ * the root's HBM: free at 2 GPUs, but 32-byte remote stores from 7 GPUs into one collapse to ~220 GB/s at 8).
+ * Handles travel between the processes by any byte channel (the Python host side uses torch.distributed). */
 #define B200AA_IPC_HANDLE_BYTES 64
 int b200aa_peer_buffer_create(size_t bytes, void **d_out, unsigned char *handle_out /* [64] */);
 int b200aa_peer_buffer_open(const unsigned char *handle /* [64] */, void **d_out);
+int b200aa_peer_copy(void *d_dst /* peer-mapped or local */, const void *d_src, size_t bytes, void *stream);
 int b200aa_peer_buffer_close(void *d_ptr, int owner /* 1: the creating rank (frees), 0: a mapping rank (unmaps) */);
 
 /* debugging: when set (device pointer, float32 [n_clips, t_stride, K]) the pair kernel also dumps its |X| rows */

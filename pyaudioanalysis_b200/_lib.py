@@ -53,6 +53,7 @@ SIGNATURES = {
     "b200aa_host_free": (c_int, [c_vp]),
     "b200aa_peer_buffer_create": (c_int, [ctypes.c_size_t, ctypes.POINTER(c_vp), c_vp]),
     "b200aa_peer_buffer_open": (c_int, [c_vp, ctypes.POINTER(c_vp)]),
+    "b200aa_peer_copy": (c_int, [c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "b200aa_peer_buffer_close": (c_int, [c_vp, c_int]),
     "b200aa_launch_count": (c_i64, []),
 }

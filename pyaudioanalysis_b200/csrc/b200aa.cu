@@ -1108,6 +1108,14 @@ extern "C" int b200aa_peer_buffer_open(const unsigned char *handle, void **d_out
     CK(cudaIpcOpenMemHandle(d_out, h, cudaIpcMemLazyEnablePeerAccess));
     return B200AA_OK;
 }
+extern "C" int b200aa_peer_copy(void *d_dst, const void *d_src, size_t bytes, void *stream)
+{
+    if (!d_dst || !d_src) return B200AA_ERR_INVALID;
+    if (bytes == 0) return B200AA_OK;
+    // unified addressing: the copy engines move the block over NVLink, no SM on either side is involved
+    CK(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    return B200AA_OK;
+}
 extern "C" int b200aa_peer_buffer_close(void *d_ptr, int owner)
 {
     if (!d_ptr) return B200AA_OK;

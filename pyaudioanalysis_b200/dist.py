@@ -4,8 +4,12 @@ Clips are independent (no state crosses feature_extraction calls), so the path s
 the only exchange is the final gather of the per-rank [clips, F, T] blocks on one rank.  Two forms:
 
 * ``gather="p2p"`` (GPUs): the root owns one [n_clips, F, T] buffer, every other rank maps it over NVLink
-  (``b200aa_peer_buffer_*``, CUDA IPC) and its feature kernel writes its slice directly -- the gather is fused into the
-  kernel's tile store: no collective kernel, no copy, no SMs taken on the root;
+  (``b200aa_peer_buffer_*``, CUDA IPC) and pushes its finished block into its slice with the copy engines
+  (``b200aa_peer_copy``): no collective kernel, no SMs taken on either side, and in a loop the push of batch i rides
+  under the kernels of batch i + 1;
+* ``gather="p2p_store"``: the feature kernel writes its slice of the mapped buffer directly (gather fused into the tile
+  store).  Free at 2 GPUs, but 32-byte remote stores from 7 GPUs into one root collapse to ~220 GB/s of ingress at 8
+  (profiles/bench_r2_n8_fused.json), so it is not the default;
 * ``gather="nccl"`` / gloo: ``torch.distributed.gather`` of padded blocks (the baseline, and what the CPU tests run).
 """
 import ctypes
@@ -91,6 +95,17 @@ class PeerGather:
             return DeviceBuffer(self.ptr + 4 * lo * F * T, (hi - lo, F, T))
         return torch.as_tensor(_DevicePtr(self.ptr + 4 * lo * F * T, (hi - lo, F, T)), device=self.device)
 
+    def push(self, local, lo, stream=None):
+        """Copy this rank's finished block ``local`` ([n, F, T] float32 CUDA tensor) into clips lo.. of the buffer with the
+        copy engines, asynchronously on ``stream`` (default: the current stream)."""
+        n, F, T = self.shape
+        if local.dtype != torch.float32 or not local.is_contiguous() or tuple(local.shape[1:]) != (F, T) or lo + local.shape[0] > n:
+            raise ValueError("block does not fit the gather buffer")
+        st = torch.cuda.current_stream() if stream is None else stream
+        from ._lib import check
+        check(self._L.b200aa_peer_copy(ctypes.c_void_p(self.ptr + 4 * lo * F * T), ctypes.c_void_p(local.data_ptr()),
+                                       4 * local.numel(), ctypes.c_void_p(st.cuda_stream)))
+
     def finish(self):
         torch.cuda.current_stream().synchronize()      # this rank's kernels (and their remote stores) are complete
         dist.barrier(group=self.group)
@@ -114,13 +129,12 @@ def feature_extraction_sharded(all_clips_fn, n_clips, sampling_rate, window, ste
 
     ``all_clips_fn(lo, hi)`` returns this rank's clips [hi-lo, N] on its device; ``compute`` defaults to the GPU path
     (``feature_extraction_batch``) and is injectable so the sharding logic can be tested on CPU with gloo.
-    ``gather="p2p"``: the kernel stores straight into the root's peer-mapped buffer (GPUs of one box only); the
-    returned tensor on the root then aliases that buffer (keep the result or clone it before the next call).
+    ``gather="p2p"`` / ``"p2p_store"``: through the root's peer-mapped buffer (GPUs of one box only), see the module text.
     """
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     lo, hi = shard_bounds(n_clips, rank, world)
     clips = all_clips_fn(lo, hi)
-    if gather == "p2p" and gather_to is not None and compute is None:
+    if gather in ("p2p", "p2p_store") and gather_to is not None and compute is None:
         from .batch import feature_extraction_batch
         from ._lib import lib
         T = lib().b200aa_num_frames(int(clips.shape[-1]), int(window), int(step))
@@ -128,7 +142,10 @@ def feature_extraction_sharded(all_clips_fn, n_clips, sampling_rate, window, ste
             raise ValueError("need at least one array to concatenate")
         pg = PeerGather(n_clips, 68 if deltas else 34, T, dst=gather_to, group=group)
         if hi > lo:
-            feature_extraction_batch(clips, sampling_rate, window, step, deltas=deltas, out=pg.view(lo, hi))
+            if gather == "p2p_store" or pg.owner:
+                feature_extraction_batch(clips, sampling_rate, window, step, deltas=deltas, out=pg.view(lo, hi))
+            else:
+                pg.push(feature_extraction_batch(clips, sampling_rate, window, step, deltas=deltas), lo)
         res = pg.finish()
         if res is not None:
             res = res.clone()

@@ -29,7 +29,7 @@ def main():
         return torch.from_numpy(np.stack([O.synth_clip(500 + i, n, fs) for i in range(lo, hi)])).cuda()
 
     refs = [O.feature_extraction(O.synth_clip(500 + i, n, fs), fs, w, s)[0] for i in range(n_clips)] if rank == 0 else None
-    for mode in ("nccl", "p2p"):          # the collective baseline, and the kernel storing into the root's peer-mapped buffer
+    for mode in ("nccl", "p2p", "p2p_store"):      # collective baseline; copy-engine push / kernel stores into the root's peer-mapped buffer
         got = feature_extraction_sharded(clips, n_clips, fs, w, s, deltas=True, gather_to=0, gather=mode)
         if rank == 0:
             assert got.shape == (n_clips, 68, (n - w) // s + 1), got.shape
