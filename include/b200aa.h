@@ -84,9 +84,10 @@ int64_t b200aa_mid_windows(int64_t n_frames, int step_ratio);                  /
 int  b200aa_plan_create(b200aa_plan **out, int fs, int window, int step);
 void b200aa_plan_destroy(b200aa_plan *plan);
 /* kernel that feature launches of this plan use: 0 = generic mixed-radix kernel (any window), 1 = register-tiled
- * CTA kernel (windows 320/400/480/600/640/800/882), 2 = warp-autonomous pair kernel (windows 32*R: 320/480/640/800/960) */
+ * CTA kernel (windows 320/400/480/600/640/800/882), 2 = warp-autonomous pair kernel (windows 32*R: 320/480/512/640/
+ * 800/960/1024), 3 = warp-autonomous per-frame kernel (windows 882/400/600, also their spectrogram / chromagram rows) */
 int  b200aa_plan_kernel_kind(const b200aa_plan *plan);
-/* restrict the plan to one kernel (testing / A-B runs): -1 = automatic (default), 0, 1 or 2 as above; a kind that
+/* restrict the plan to one kernel (testing / A-B runs): -1 = automatic (default), 0..3 as above; a kind that
  * does not exist for the plan's window falls through to the next one */
 int  b200aa_plan_prefer_kernel(b200aa_plan *plan, int kind);
 /* force the generic kernel (testing): returns the previous setting */

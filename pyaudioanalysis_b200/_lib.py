@@ -112,7 +112,8 @@ class Plan:
         return lib().b200aa_plan_force_generic(self.handle, 1 if on else 0)
 
     def prefer_kernel(self, kind):
-        """-1 automatic, 0 generic, 1 register-tiled CTA kernel, 2 warp-autonomous pair kernel (testing / A-B)."""
+        """-1 automatic, 0 generic, 1 register-tiled CTA kernel, 2 warp-autonomous pair kernel, 3 warp-autonomous per-frame
+        kernel (testing / A-B)."""
         check(lib().b200aa_plan_prefer_kernel(self.handle, int(kind)))
         return self
 

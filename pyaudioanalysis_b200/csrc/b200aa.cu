@@ -19,6 +19,7 @@
 #include "generic_kernel.cuh"
 #include "fast_kernel.cuh"
 #include "pair_kernel.cuh"
+#include "solo_kernel.cuh"
 #include "tables.inl"
 
 using namespace b200aa;
@@ -149,7 +150,8 @@ struct b200aa_plan {
     size_t ws_cap[4] = {0, 0, 0, 0};
     FastTables fast{};                  // extra device tables of the specialised kernel
     PairTables pair{};                  // inter-pass twiddles of the warp-autonomous pair kernel (windows 32 * R)
-    int prefer = -1;                    // -1 = automatic, 0 / 1 / 2 = generic / register-tiled / pair kernel only (testing, A/B)
+    SoloTables solo{};                  // tables of the warp-autonomous per-frame kernel (windows 882 / 400 / 600)
+    int prefer = -1;                    // -1 = automatic, 0 / 1 / 2 / 3 = generic / register-tiled CTA / pair / solo kernel only (testing, A/B)
     // ring of work counters (one per in-flight launch of a persistent kernel).  A slot is handed out again only after
     // the launch that used it last has finished: that launch recorded the slot's event, the next user's stream waits on it.
     static constexpr unsigned kSlots = 256;
@@ -172,6 +174,7 @@ struct b200aa_plan {
         }
         fast.release();
         pair.release();
+        solo.release();
         if (d_counters) cudaFree(d_counters);
         for (cudaEvent_t e : slot_event) if (e) cudaEventDestroy(e);
     }
@@ -305,7 +308,8 @@ extern "C" int b200aa_plan_create(b200aa_plan **out, int fs, int window, int ste
     if (rc != B200AA_OK) return rc;
     rc = fast_plan_init(fs, window, step, pl->h_blob, pl->bl, &pl->fast, &pl->fast_kind);
     if (rc != B200AA_OK) return rc;
-    if (pair_r_for_window(window) && pl->tables_status == B200AA_OK) {
+    int sl_ = 0, sr_ = 0;
+    if ((pair_r_for_window(window) || solo_shape_for_window(window, &sl_, &sr_)) && pl->tables_status == B200AA_OK) {
         std::vector<double> mel, chr, dct;
         b200aa_host::build_mel(fs, pl->K, mel);
         b200aa_host::build_chroma(fs, pl->K, chr);
@@ -315,6 +319,8 @@ extern "C" int b200aa_plan_create(b200aa_plan **out, int fs, int window, int ste
         build_pair_blob(mel, chr, dct, pl->K, pblob, pbl);
         rc = pair_plan_init(window, pblob, pbl, &pl->pair);
         if (rc != B200AA_OK) return cuda_fail(cudaGetLastError(), "pair_plan_init");
+        rc = solo_plan_init(window, pblob, pbl, &pl->solo);
+        if (rc != B200AA_OK) return cuda_fail(cudaGetLastError(), "solo_plan_init");
     }
     CK(cudaMalloc(&pl->d_counters, b200aa_plan::kSlots * sizeof(unsigned int)));
     *out = pl.release();
@@ -342,15 +348,16 @@ static int slot_done(b200aa_plan *pl, cudaStream_t st, unsigned slot)
 }
 
 static bool use_pair(const b200aa_plan *pl) { return pl->pair.R && !pl->force_generic && (pl->prefer < 0 || pl->prefer == 2); }
+static bool use_solo(const b200aa_plan *pl) { return pl->solo.L && !pl->force_generic && (pl->prefer < 0 || pl->prefer == 3); }
 static bool use_fast(const b200aa_plan *pl) { return pl->fast_kind && !pl->force_generic && (pl->prefer < 0 || pl->prefer == 1); }
 extern "C" int b200aa_plan_kernel_kind(const b200aa_plan *plan)
 {
     if (!plan) return 0;
-    return use_pair(plan) ? 2 : (use_fast(plan) ? 1 : 0);
+    return use_pair(plan) ? 2 : (use_solo(plan) ? 3 : (use_fast(plan) ? 1 : 0));
 }
 extern "C" int b200aa_plan_prefer_kernel(b200aa_plan *plan, int kind)
 {
-    if (!plan || kind < -1 || kind > 2) return B200AA_ERR_INVALID;
+    if (!plan || kind < -1 || kind > 3) return B200AA_ERR_INVALID;
     plan->prefer = kind;
     return B200AA_OK;
 }
@@ -776,6 +783,15 @@ extern "C" int b200aa_st_features(const b200aa_plan *plan, const void *d_sig, in
         if (rc == B200AA_OK) { g_launches.fetch_add(1, std::memory_order_relaxed); return rc2; }
         if (rc != B200AA_ERR_UNSUPPORTED) return rc == B200AA_ERR_CUDA ? cuda_fail(cudaGetLastError(), "pair kernel") : rc;
     }
+    if (use_solo(pl)) {
+        unsigned slot = 0;
+        unsigned int *ctr = nullptr;
+        if ((rc = slot_acquire(pl, st, &slot, &ctr)) != B200AA_OK) return rc;
+        rc = solo_launch_mode<kModeFeatures>(pl->solo, p, pl->sm_count, T, ctr, st);
+        const int rc2 = slot_done(pl, st, slot);
+        if (rc == B200AA_OK) { g_launches.fetch_add(1, std::memory_order_relaxed); return rc2; }
+        if (rc != B200AA_ERR_UNSUPPORTED) return rc == B200AA_ERR_CUDA ? cuda_fail(cudaGetLastError(), "solo kernel") : rc;
+    }
     if (use_fast(pl)) {
         unsigned slot = 0;
         unsigned int *ctr = nullptr;
@@ -810,7 +826,17 @@ extern "C" int b200aa_spectrogram(const b200aa_plan *plan, const void *d_sig, in
     p.mode = kModeSpectrogram;
     p.origin = w; p.row0 = 0; p.rows_total = R; p.rows_launch = R;
     p.rows_valid = std::min<int64_t>(R, b200aa_host::range_len(w, n_samples - w + 1, s));   // :415
-    if (pl->fast_kind && !pl->force_generic && pl->prefer != 0) {
+    if (use_solo(pl)) {
+        cudaStream_t st_ = static_cast<cudaStream_t>(stream);
+        unsigned slot = 0;
+        unsigned int *ctr = nullptr;
+        if ((rc = slot_acquire(pl, st_, &slot, &ctr)) != B200AA_OK) return rc;
+        rc = solo_launch_mode<kModeSpectrogram>(pl->solo, p, pl->sm_count, p.rows_launch, ctr, st_);
+        const int rc2 = slot_done(pl, st_, slot);
+        if (rc == B200AA_OK) { g_launches.fetch_add(1, std::memory_order_relaxed); return rc2; }
+        if (rc != B200AA_ERR_UNSUPPORTED) return rc == B200AA_ERR_CUDA ? cuda_fail(cudaGetLastError(), "solo kernel") : rc;
+    }
+    if (pl->fast_kind && !pl->force_generic && pl->prefer != 0 && pl->prefer != 3) {
         cudaStream_t st_ = static_cast<cudaStream_t>(stream);
         unsigned slot = 0;
         unsigned int *ctr = nullptr;
@@ -851,7 +877,16 @@ extern "C" int b200aa_chromagram(const b200aa_plan *plan, const void *d_sig, int
     p.mode = kModeChromagram;
     p.origin = w; p.row0 = 0; p.rows_total = R; p.rows_launch = R; p.rows_valid = n_full;
     rc = B200AA_ERR_UNSUPPORTED;
-    if (pl->fast_kind && !pl->force_generic && pl->prefer != 0) {
+    if (use_solo(pl)) {
+        unsigned slot = 0;
+        unsigned int *ctr = nullptr;
+        if ((rc = slot_acquire(pl, st, &slot, &ctr)) != B200AA_OK) return rc;
+        rc = solo_launch_mode<kModeChromagram>(pl->solo, p, pl->sm_count, p.rows_launch, ctr, st);
+        if (slot_done(pl, st, slot) != B200AA_OK) return B200AA_ERR_CUDA;
+        if (rc == B200AA_OK) g_launches.fetch_add(1, std::memory_order_relaxed);
+        else if (rc != B200AA_ERR_UNSUPPORTED) return rc == B200AA_ERR_CUDA ? cuda_fail(cudaGetLastError(), "solo kernel") : rc;
+    }
+    if (rc == B200AA_ERR_UNSUPPORTED && pl->fast_kind && !pl->force_generic && pl->prefer != 0 && pl->prefer != 3) {
         unsigned slot = 0;
         unsigned int *ctr = nullptr;
         if ((rc = slot_acquire(pl, st, &slot, &ctr)) != B200AA_OK) return rc;

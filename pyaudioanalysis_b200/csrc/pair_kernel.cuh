@@ -414,6 +414,107 @@ __device__ __forceinline__ void frame_scale(float E, float inv_a2n, float &s, fl
     inv_s = __int_as_float((127 - k) << 23);
 }
 
+// tables of the feature phases in shared memory
+struct FeatTables {
+    const float *dct;
+    const int *mrec;
+    const float4 *mw;
+    const int2 *chr;
+    int LQ, CT;
+};
+
+// ----------------------------------------------------------------------------------------------
+// |X| rows of two frames (a: lanes 0-15, b: lanes 16-31) -> feature slots 3..33 of fva / fvb:
+// spectral rows (pair_spectral), mel filters + log10, folded DCT-II, chroma.  Xprev = the row before frame a
+// (frame a itself when there is none); frame b's predecessor is frame a.
+// ----------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void rows_to_features(const float *Xa, const float *Xb, const float *Xprev, bool fresh, float carried,
+                                                 const int *dlane, float *parts, float *msraw, float *mslog, float *mfold, float *chr,
+                                                 float *fva, float *fvb, const FeatTables &ft, int lane)
+{
+    const int half = lane >> 4, l16 = lane & 15;
+    const unsigned FULLM = 0xffffffffu;
+    {
+        const float *X = half ? Xb : Xa;
+        const float *Xp = half ? Xa : Xprev;
+        pair_spectral<K>(X, Xp, carried, fresh, dlane + l16 * 4, parts + half * 32, half ? fvb : fva, l16, half);
+    }
+    // ---- mel filters: 16 lanes per frame, LQ steps of four taps each (whole filters per lane, balanced on the host);
+    //      raw chroma sums: 12 lanes per frame, CT taps each
+    {
+        const float *X = half ? Xb : Xa;
+        float acc = 0.f;
+#pragma unroll 4
+        for (int q = 0; q < ft.LQ; ++q) {
+            const int rec = ft.mrec[q * 16 + l16];
+            const float4 w = ft.mw[q * 16 + l16];
+            const float *xp = X + (rec & 0xffff);
+            acc = fmaf(xp[0], w.x, acc);
+            acc = fmaf(xp[1], w.y, acc);
+            acc = fmaf(xp[2], w.z, acc);
+            acc = fmaf(xp[3], w.w, acc);
+            if (rec & (1 << 24)) { msraw[half * B200AA_N_MEL + ((rec >> 16) & 0xff)] = acc; acc = 0.f; }
+        }
+        float ch = 0.f;
+        for (int t = 0; t < ft.CT; ++t) {
+            const int2 e = ft.chr[t * 16 + l16];
+            const float v = X[e.x];
+            ch = fmaf(v * v, __int_as_float(e.y), ch);
+        }
+        if (l16 < 12) chr[half * 12 + l16] = ch;
+    }
+    __syncwarp();
+    // ---- log10, fold (m_n - k) +- (m_(39-n) - k) with k = m_0 (see flat_dct in fast_kernel.cuh), 13 x 20 DCT rows
+#pragma unroll
+    for (int t = lane; t < 2 * B200AA_N_MEL; t += 32) mslog[t] = 0.30102999566398120f * flog2(msraw[t] + B200AA_EPS);
+    __syncwarp();
+#pragma unroll
+    for (int t = lane; t < 2 * B200AA_N_MEL; t += 32) {
+        const int f = t >= B200AA_N_MEL ? 1 : 0, r = t - f * B200AA_N_MEL;
+        const int kind = r >= 20 ? 1 : 0, n = r - 20 * kind;
+        const float *m = mslog + f * B200AA_N_MEL;
+        const float a = m[n], bq = m[39 - n], kap = m[0];
+        mfold[t] = kind ? a - bq : (a - kap) + (bq - kap);
+    }
+    __syncwarp();
+    {
+        const int c = l16 < B200AA_N_MFCC ? l16 : 0;
+        const float *src = mfold + half * B200AA_N_MEL + 20 * (c & 1);
+        const float *row = ft.dct + c * 41;
+        float acc = 0.f;
+#pragma unroll
+        for (int n = 0; n < 20; ++n) acc = fmaf(row[n], src[n], acc);
+        if (c == 0) acc = fmaf(6.324555320336759f, mslog[half * B200AA_N_MEL], acc);      // sqrt(1/40) * 40 * k
+        if (l16 < B200AA_N_MFCC) (half ? fvb : fva)[8 + c] = acc;
+    }
+    chroma_finalize_h(chr + half * 12, half ? fvb : fva, l16, true);
+    __syncwarp();
+    (void)FULLM;
+}
+
+// [<= 8 frames x n_out] tile of a warp -> global memory: lane -> (feature row f0 + 4 i, frame c): eight consecutive lanes
+// write 32 consecutive bytes of one output row; deltas on the fly against the previous row (row 0 of fv = the frame
+// before the tile)
+__device__ __forceinline__ void tile_store(const float *fv, int tile_n, int tile_t0, float *out_clip, int64_t t_stride, int n_out, int lane)
+{
+    const int c = lane & 7, f0 = lane >> 3;
+    if (c < tile_n) {
+        float *const out_b = out_clip + tile_t0 + c;
+        const float *cur_row = fv + (1 + c) * kFvStride, *prv_row = fv + c * kFvStride;
+        const bool first = tile_t0 + c == 0;              // frame 0 of the clip: deltas are zero
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const int f = f0 + 4 * i;
+            if (f < B200AA_N_BASE) {
+                const float v = cur_row[f];
+                out_b[size_t(f) * t_stride] = v;
+                if (n_out > B200AA_N_BASE) out_b[size_t(f + B200AA_N_BASE) * t_stride] = first ? 0.f : v - prv_row[f];
+            }
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------------------------
 // kernel
 // ----------------------------------------------------------------------------------------------
@@ -437,7 +538,7 @@ __global__ void __launch_bounds__(32 * pair_warps<R>(), kPairMinBlocks) st_pair_
     const int *const t_mrec = blob_s + pp.pbl.mel_rec;
     const float4 *const t_mw = reinterpret_cast<const float4 *>(blob_s + pp.pbl.mel_w);
     const int2 *const t_chr = reinterpret_cast<const int2 *>(blob_s + pp.pbl.chr);
-    const int LQ = pp.pbl.lq, CT = pp.pbl.ct;
+    const FeatTables ftab{t_dct, t_mrec, t_mw, t_chr, pp.pbl.lq, pp.pbl.ct};
     PairWarpMem<R> &wm = cm_.w[warp];
     float *const rowa = reinterpret_cast<float *>(wm.tz);
     float *const t_re = reinterpret_cast<float *>(wm.tz), *const t_im = t_re + R * LS;
@@ -688,84 +789,15 @@ __global__ void __launch_bounds__(32 * pair_warps<R>(), kPairMinBlocks) st_pair_
                 }
             }
             __syncwarp();
-            // ---- spectral rows: half-warp per frame
-            {
-                const float *X = half ? rowbn : rowa;
-                const float *Xp = half ? rowa : (fresh ? rowa : wm.rowb[cur ^ 1]);
-                const float carried = wm.fv[(ra - 1) * kFvStride + 34];          // row sum of the previous pair's b (unused when fresh)
-                pair_spectral<K>(X, Xp, carried, fresh, cm_.dlane + l16 * 4, wm.parts + half * 32, half ? fvb : fva, l16, half);
-            }
-            // ---- mel filters: 16 lanes per frame, LQ steps of four taps each (whole filters per lane, balanced on the host);
-            //      raw chroma sums: 12 lanes per frame, CT taps each
-            {
-                const float *X = half ? rowbn : rowa;
-                float acc = 0.f;
-#pragma unroll 4
-                for (int q = 0; q < LQ; ++q) {
-                    const int rec = t_mrec[q * 16 + l16];
-                    const float4 w = t_mw[q * 16 + l16];
-                    const float *xp = X + (rec & 0xffff);
-                    acc = fmaf(xp[0], w.x, acc);
-                    acc = fmaf(xp[1], w.y, acc);
-                    acc = fmaf(xp[2], w.z, acc);
-                    acc = fmaf(xp[3], w.w, acc);
-                    if (rec & (1 << 24)) { msraw[half * B200AA_N_MEL + ((rec >> 16) & 0xff)] = acc; acc = 0.f; }
-                }
-                float ch = 0.f;
-                for (int t = 0; t < CT; ++t) {
-                    const int2 e = t_chr[t * 16 + l16];
-                    const float v = X[e.x];
-                    ch = fmaf(v * v, __int_as_float(e.y), ch);
-                }
-                if (l16 < 12) wm.chr[half * 12 + l16] = ch;
-            }
-            __syncwarp();
-            // ---- log10, fold (m_n - k) +- (m_(39-n) - k) with k = m_0 (see flat_dct in fast_kernel.cuh), 13 x 20 DCT rows
-#pragma unroll
-            for (int t = lane; t < 2 * B200AA_N_MEL; t += 32) mslog[t] = 0.30102999566398120f * flog2(msraw[t] + B200AA_EPS);
-            __syncwarp();
-#pragma unroll
-            for (int t = lane; t < 2 * B200AA_N_MEL; t += 32) {
-                const int f = t >= B200AA_N_MEL ? 1 : 0, r = t - f * B200AA_N_MEL;
-                const int kind = r >= 20 ? 1 : 0, n = r - 20 * kind;
-                const float *m = mslog + f * B200AA_N_MEL;
-                const float a = m[n], bq = m[39 - n], kap = m[0];
-                mfold[t] = kind ? a - bq : (a - kap) + (bq - kap);
-            }
-            __syncwarp();
-            {
-                const int c = l16 < B200AA_N_MFCC ? l16 : 0;
-                const float *src = mfold + half * B200AA_N_MEL + 20 * (c & 1);
-                const float *row = t_dct + c * 41;
-                float acc = 0.f;
-#pragma unroll
-                for (int n = 0; n < 20; ++n) acc = fmaf(row[n], src[n], acc);
-                if (c == 0) acc = fmaf(6.324555320336759f, mslog[half * B200AA_N_MEL], acc);      // sqrt(1/40) * 40 * k
-                if (l16 < B200AA_N_MFCC) (half ? fvb : fva)[8 + c] = acc;
-            }
-            chroma_finalize_h(wm.chr + half * 12, half ? fvb : fva, l16, true);
-            __syncwarp();
+            // ---- spectral rows, mel / chroma / DCT: half-warp per frame over the two |X| rows
+            rows_to_features<K>(rowa, rowbn, fresh ? rowa : wm.rowb[cur ^ 1], fresh, wm.fv[(ra - 1) * kFvStride + 34], cm_.dlane,
+                                wm.parts, msraw, mslog, mfold, wm.chr, fva, fvb, ftab, lane);
 
             // ---- tile bookkeeping / store
             if (store) {
                 tile_n += bvalid ? 2 : 1;
                 if (tile_n == 8 || q == q1 - 1) {
-                    // lane -> (feature row f0 + 4 i, frame c): eight consecutive lanes write 32 consecutive bytes of one output row
-                    const int c = lane & 7, f0 = lane >> 3;
-                    if (c < tile_n) {
-                        float *const out_b = p.out + size_t(b) * p.n_out * p.t_stride + tile_t0 + c;
-                        const float *cur_row = wm.fv + (1 + c) * kFvStride, *prv_row = wm.fv + c * kFvStride;
-                        const bool first = tile_t0 + c == 0;              // frame 0 of the clip: deltas are zero
-#pragma unroll
-                        for (int i = 0; i < 9; ++i) {
-                            const int f = f0 + 4 * i;
-                            if (f < B200AA_N_BASE) {
-                                const float v = cur_row[f];
-                                out_b[size_t(f) * p.t_stride] = v;
-                                if (p.n_out > B200AA_N_BASE) out_b[size_t(f + B200AA_N_BASE) * p.t_stride] = first ? 0.f : v - prv_row[f];
-                            }
-                        }
-                    }
+                    tile_store(wm.fv, tile_n, tile_t0, p.out + size_t(b) * p.n_out * p.t_stride, p.t_stride, p.n_out, lane);
                     __syncwarp();
                     wm.fv[lane] = wm.fv[tile_n * kFvStride + lane];
                     if (lane < 4) wm.fv[32 + lane] = wm.fv[tile_n * kFvStride + 32 + lane];     // incl. the row sum (slot 34)

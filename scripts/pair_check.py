@@ -42,13 +42,17 @@ def main():
     ok = True
     cases = [(16000, 800, 400, 48000), (16000, 800, 400, 32400), (16000, 800, 200, 20000), (16000, 800, 800, 24000), (16000, 800, 333, 20000),
              (16000, 320, 160, 12000), (16000, 480, 240, 14000), (16000, 640, 320, 20000), (16000, 640, 160, 12000),
-             (16000, 960, 480, 30000), (48000, 960, 960, 40000), (16000, 1024, 512, 30000), (16000, 512, 256, 20000), (16000, 1024, 256, 20000), (8000, 320, 80, 8000), (16000, 800, 400, 800), (16000, 800, 400, 1200)]
+             (16000, 960, 480, 30000), (48000, 960, 960, 40000), (16000, 1024, 512, 30000), (16000, 512, 256, 20000), (16000, 1024, 256, 20000), (8000, 320, 80, 8000), (16000, 800, 400, 800), (16000, 800, 400, 1200),
+             (44100, 882, 441, 50000), (44100, 882, 882, 30000), (44100, 882, 300, 20000), (16000, 400, 160, 20000), (16000, 400, 200, 12000),
+             (8000, 600, 300, 12000), (44100, 882, 441, 882), (44100, 882, 441, 1323)]
     for fs, w, s, n in cases:
         x = O.synth_clip(100 + w + s, n, fs)
         ref = O.feature_extraction(x, fs, w, s)[0]
         d = torch.from_numpy(x).cuda()[None]
-        for kind in (2, 1, 0):
+        for kind in (2, 3, 1, 0):
             pl = Plan(fs, w, s).prefer_kernel(kind)
+            if pl.kernel_kind() != kind:
+                continue
             got = pkg.feature_extraction_batch(d, fs, w, s, plan=pl)[0].cpu().numpy()
             ok &= report("fs=%d w=%d s=%d n=%d kernel %d(%d)" % (fs, w, s, n, kind, pl.kernel_kind()), got, ref, w // 2)
     # quiet / loud neighbours, silence, DC offset, float input, integer mean (two-sided sign masks)
@@ -111,11 +115,13 @@ def main():
         ms = e0.elapsed_time(e1) / 10
         print(json.dumps({"kernel": kind, "seg": env, "ms": ms, "Mframes_per_s": 399000 / ms / 1e3}))
     os.environ.pop("B200AA_PAIR_SEG", None)
-    for w, s_ in ((1024, 512), (512, 256), (640, 320), (960, 480), (320, 160)):
+    for w, s_ in ((1024, 512), (512, 256), (400, 160), (400, 200)):
         T = (160000 - w) // s_ + 1
         o2 = torch.empty((1000, 68, T), device="cuda")
-        for kind in (2, 0):
+        for kind in (2, 3, 1):
             pl = Plan(16000, w, s_).prefer_kernel(kind)
+            if pl.kernel_kind() != kind:
+                continue
             for _ in range(2):
                 pkg.feature_extraction_batch(c2, 16000, w, s_, out=o2, norm=norm, plan=pl)
             torch.cuda.synchronize()
@@ -127,6 +133,26 @@ def main():
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 5
             print(json.dumps({"window": w, "step": s_, "kernel": pl.kernel_kind(), "ms": ms, "Mframes_per_s": 1000 * T / ms / 1e3}))
+    # config 3 shape: 16 x 60 s @44.1 kHz, 882 / 441, per kernel kind and mode
+    c3 = (3000.0 * torch.randn((16, 2646000), generator=g, device="cuda")).round().clamp(-32768, 32767).to(torch.int16)
+    for kind in (3, 1):
+        pl = Plan(44100, 882, 441).prefer_kernel(kind)
+        row = {"config3_kernel": pl.kernel_kind()}
+        for name, fn in (("features", lambda: pkg.feature_extraction_batch(c3, 44100, 882, 441, plan=pl)),
+                         ("spectrogram", lambda: pkg.spectrogram_batch(c3, 44100, 882, 441, plan=pl)),
+                         ("chromagram", lambda: pkg.chromagram_batch(c3, 44100, 882, 441, plan=pl))):
+            fn(); fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            row[name + "_ms"] = ms
+            row[name + "_Mrows_per_s"] = 16 * 5999 / ms / 1e3
+        print(json.dumps(row))
     print("ALL OK" if ok else "SOME BAD")
 
 

@@ -193,6 +193,7 @@ int main()
     check_codelet<10>(); check_codelet<12>(); check_codelet<15>(); check_codelet<16>(); check_codelet<20>(); check_codelet<21>();
     check_shape<20, 20>(); check_shape<21, 21>(); check_shape<20, 10>(); check_shape<20, 12>();
     check_shape<20, 15>(); check_shape<16, 10>(); check_shape<20, 16>();
+    check_shape<10, 20>(); check_shape<15, 20>();     // the solo kernel's 400 / 600 windows (R1 = points per lane, R2 = lanes)
     printf("worst %.3e\n", g_worst);
     return g_worst < 2e-6 ? 0 : 1;
 }

@@ -312,19 +312,19 @@ def test_mid_pool_kernel(P):
 
 
 def test_kernel_kinds_agree(P):
-    """Every kernel that exists for a window (2 = warp-autonomous pair kernel, 1 = register-tiled CTA kernel, 0 = generic)
-    must agree with the oracle; the default plan picks the fastest one."""
+    """Every kernel that exists for a window (2 = warp-autonomous pair kernel, 3 = warp-autonomous per-frame ("solo") kernel,
+    1 = register-tiled CTA kernel, 0 = generic) must agree with the oracle; the default plan picks the fastest one."""
     import torch
     from pyaudioanalysis_b200._lib import Plan
     for fs, w, s in [(16000, 800, 400), (44100, 882, 441), (16000, 800, 800), (16000, 800, 200), (8000, 400, 200),
                      (16000, 400, 160), (16000, 480, 240), (8000, 600, 300), (16000, 640, 320), (16000, 320, 160),
                      (16000, 1024, 512), (16000, 512, 256), (16000, 512, 128), (48000, 960, 480), (16000, 1024, 300),
-                     (16000, 800, 333)]:
+                     (16000, 800, 333), (44100, 882, 882), (44100, 882, 300), (16000, 400, 400), (8000, 600, 150)]:
         clips = np.stack([O.synth_clip(40 + i, 24000 + 7 * i, fs)[:24000] for i in range(3)])
         d = torch.from_numpy(clips).cuda()
         refs = [O.feature_extraction(clips[i], fs, w, s)[0] for i in range(3)]
         kinds = set()
-        for prefer in (-1, 2, 1, 0):
+        for prefer in (-1, 2, 3, 1, 0):
             pl = Plan(fs, w, s).prefer_kernel(prefer)
             kind = pl.kernel_kind()
             if prefer >= 0 and kind != prefer:
@@ -336,28 +336,30 @@ def test_kernel_kinds_agree(P):
         assert 0 in kinds
         if w in (320, 480, 512, 640, 800, 960, 1024):
             assert 2 in kinds and Plan(fs, w, s).kernel_kind() == 2
+        if w in (882, 400, 600):
+            assert 3 in kinds and 1 in kinds and Plan(fs, w, s).kernel_kind() == 3
         pg = Plan(fs, w, s)
         pg.force_generic(True)
         assert pg.kernel_kind() == 0
 
 
 def test_row_kernels_agree(P):
-    """spectrogram / chromagram through the specialised kernel, the generic kernel and the oracle."""
+    """spectrogram / chromagram through the default kernel (solo for 882 / 400 / 600, CTA for 800), the CTA kernel, the
+    generic kernel, and the oracle."""
     import torch
     from pyaudioanalysis_b200._lib import Plan
     for fs, w, s, n in [(16000, 800, 400, 40000), (44100, 882, 441, 50000), (16000, 800, 800, 24000), (16000, 800, 200, 16400),
-                        (16000, 400, 160, 16000), (8000, 600, 300, 12000)]:
+                        (16000, 400, 160, 16000), (8000, 600, 300, 12000), (44100, 882, 882, 30000), (44100, 882, 300, 20001)]:
         clips = np.stack([O.synth_clip(60 + i, n, fs) for i in range(3)])
         d = torch.from_numpy(clips).cuda()
-        pf, pg = Plan(fs, w, s), Plan(fs, w, s)
-        pg.force_generic(True)
+        plans = [Plan(fs, w, s), Plan(fs, w, s).prefer_kernel(1), Plan(fs, w, s)]
+        plans[2].force_generic(True)
         for fn, ofn, atol in ((P.spectrogram_batch, O.spectrogram, 1e-7), (P.chromagram_batch, O.chromagram, 1e-6)):
-            a = fn(d, fs, w, s, plan=pf).cpu().numpy()
-            b = fn(d, fs, w, s, plan=pg).cpu().numpy()
-            for i in range(3):
-                ref = ofn(clips[i], fs, w, s)[0]
-                check_close(a[i], ref, f"{fn.__name__} default kernel fs={fs} w={w} s={s}", atol=atol)
-                check_close(b[i], ref, f"{fn.__name__} generic kernel fs={fs} w={w} s={s}", atol=atol)
+            refs = [ofn(clips[i], fs, w, s)[0] for i in range(3)]
+            for pl, what in zip(plans, ("default", "CTA", "generic")):
+                a = fn(d, fs, w, s, plan=pl).cpu().numpy()
+                for i in range(3):
+                    check_close(a[i], refs[i], f"{fn.__name__} {what} kernel fs={fs} w={w} s={s}", atol=atol)
     # a clipped last frame shorter than num_fft makes the reference's scatter raise ValueError (:288)
     bad = O.synth_clip(60, 16300, 16000)
     with pytest.raises(ValueError):
