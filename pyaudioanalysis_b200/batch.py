@@ -149,8 +149,9 @@ def mid_feature_extraction_batch(signals, sampling_rate, mid_window, mid_step, s
     return mid_pool_batch(st, ratio, stepr), st
 
 
-def spectrogram_batch(signals, sampling_rate, window, step, plan=None):
-    """CUDA [B, N] -> CUDA float32 [B, R, K] (ShortTermFeatures.py:389-452 rows, per clip)."""
+def spectrogram_batch(signals, sampling_rate, window, step, plan=None, norm=None, out=None):
+    """CUDA [B, N] -> CUDA float32 [B, R, K] (ShortTermFeatures.py:389-452 rows, per clip).  ``norm``: records of a previous
+    ``clip_stats`` call on the same clips; ``out``: a contiguous float32 [B, R, K] tensor to write into."""
     window, step = int(window), int(step)
     signals, B, N, stride, _, _ = _prep(signals, None)
     with torch.cuda.device(signals.device):
@@ -158,14 +159,18 @@ def spectrogram_batch(signals, sampling_rate, window, step, plan=None):
         R = lib().b200aa_spectrogram_rows(N, window, step)
         if R <= 0:
             check(_lib.ERR_TOO_SHORT)
-        out = torch.empty((B, R, window // 2), dtype=torch.float32, device=signals.device)
-        norm = clip_stats(signals)
+        if out is None:
+            out = torch.empty((B, R, window // 2), dtype=torch.float32, device=signals.device)
+        elif tuple(out.shape) != (B, R, window // 2) or out.dtype != torch.float32 or not out.is_contiguous() or not out.is_cuda:
+            raise ValueError("out must be a contiguous float32 CUDA tensor [B, %d, %d]" % (R, window // 2))
+        if norm is None:
+            norm = clip_stats(signals)
         check(lib().b200aa_spectrogram(plan.handle, ctypes.c_void_p(signals.data_ptr()), _dtype_code(signals), B, N, stride,
                                        ctypes.c_void_p(norm.data_ptr()), ctypes.c_void_p(out.data_ptr()), _stream()))
     return out
 
 
-def chromagram_batch(signals, sampling_rate, window, step, plan=None):
+def chromagram_batch(signals, sampling_rate, window, step, plan=None, norm=None):
     """CUDA [B, N] -> CUDA float32 [B, R, 12] (ShortTermFeatures.py:324-386 rows, per clip)."""
     window, step = int(window), int(step)
     signals, B, N, stride, _, _ = _prep(signals, None)
@@ -175,7 +180,8 @@ def chromagram_batch(signals, sampling_rate, window, step, plan=None):
         if R <= 0 or N - step - window < 0:
             check(_lib.ERR_TOO_SHORT)
         out = torch.empty((B, R, 12), dtype=torch.float32, device=signals.device)
-        norm = clip_stats(signals)
+        if norm is None:
+            norm = clip_stats(signals)
         check(lib().b200aa_chromagram(plan.handle, ctypes.c_void_p(signals.data_ptr()), _dtype_code(signals), B, N, stride,
                                       ctypes.c_void_p(norm.data_ptr()), ctypes.c_void_p(out.data_ptr()), _stream()))
     return out

@@ -238,45 +238,34 @@ __global__ void __launch_bounds__(32 * solo_warps<L, R2>(), kPairMinBlocks) st_s
             }
 
             // ---- one packed-real transform per frame
-#pragma unroll 1
-            for (int f = 0; f < 2; ++f) {
-                const int64_t s0 = f ? sb0 : sa0;
-                float *const row = f ? rowb : rowa;
-                const bool real = f ? b_real : a_real;
-                if (!real) {                   // a row the reference's loop never reaches: zeros, and no sample is touched
-                    for (int k = lane; k < Kp; k += 32) row[k] = 0.f;
-                    __syncwarp();
-                    continue;
+            // samples of a frame in transform layout: lane n2 < L holds z[L n1 + n2] = (x[2m] - x0) + i (x[2m+1] - x0), n1 < R2
+            auto load_points = [&](int64_t s0, float u0, float2 (&z)[R2]) {
+                const int n2 = lane < L ? lane : 0;
+                const float2 nu0 = make_float2(-u0, -u0);
+                if (is16) {
+#pragma unroll
+                    for (int n1 = 0; n1 < R2; ++n1) {
+                        const int64_t m = s0 + 2 * (L * n1 + n2);
+                        z[n1] = __fadd2_rn(make_float2(s16(m), s16(m + 1)), nu0);
+                    }
+                } else {
+#pragma unroll
+                    for (int n1 = 0; n1 < R2; ++n1) {
+                        const int64_t m = s0 + 2 * (L * n1 + n2);
+                        z[n1] = __fadd2_rn(make_float2(s32(m), s32(m + 1)), nu0);
+                    }
                 }
-                const float u0 = is16 ? s16(s0) : s32(s0);
-                // pass 1: lane n2 < L, R2 points z[L n1 + n2] = (x[2m] - x0) + i (x[2m+1] - x0)
-                {
-                    float2 z[R2];
-                    const int n2 = lane < L ? lane : 0;
-                    const float2 nu0 = make_float2(-u0, -u0);
-                    if (is16) {
+            };
+            // both passes + post-processing; the |X| row goes to shared memory, or (gdst != nullptr) straight to global memory
+            auto transform = [&](float2 (&z)[R2], float u0, float *row, float *gdst) {
+                fft_r<R2>(z);
+                if (lane < L) {
+                    wm.tz[lane] = z[0];
 #pragma unroll
-                        for (int n1 = 0; n1 < R2; ++n1) {
-                            const int64_t m = s0 + 2 * (L * n1 + n2);
-                            z[n1] = __fadd2_rn(make_float2(s16(m), s16(m + 1)), nu0);
-                        }
-                    } else {
-#pragma unroll
-                        for (int n1 = 0; n1 < R2; ++n1) {
-                            const int64_t m = s0 + 2 * (L * n1 + n2);
-                            z[n1] = __fadd2_rn(make_float2(s32(m), s32(m + 1)), nu0);
-                        }
-                    }
-                    fft_r<R2>(z);
-                    if (lane < L) {
-                        wm.tz[lane] = z[0];
-#pragma unroll
-                        for (int k1 = 1; k1 < R2; ++k1) wm.tz[k1 * TS + lane] = cmul(z[k1], cm_.tw[k1 * L + lane]);
-                    }
+                    for (int k1 = 1; k1 < R2; ++k1) wm.tz[k1 * TS + lane] = cmul(z[k1], cm_.tw[k1 * L + lane]);
                 }
                 __syncwarp();
-                // pass 2: lane k1 < R2, L points over n2 -> Z[k1 + R2 k2]
-                {
+                {   // pass 2: lane k1 < R2, L points over n2 -> Z[k1 + R2 k2]
                     float2 v[L];
                     const int k1 = lane < R2 ? lane : 0;
 #pragma unroll
@@ -290,7 +279,7 @@ __global__ void __launch_bounds__(32 * solo_warps<L, R2>(), kPairMinBlocks) st_s
                 }
                 __syncwarp();
                 // post-processing: (Z[k], Z[Nc-k]) -> |X[k]|, |X[Nc-k]|  (X = ev + W_N^k od, X' = conj(ev - W_N^k od))
-                const float scf = sc;
+                float *const dst = gdst ? gdst : row;
 #pragma unroll
                 for (int j = 0; j < (KH + 31) / 32; ++j) {
                     const int k = 1 + lane + 32 * j;
@@ -300,31 +289,54 @@ __global__ void __launch_bounds__(32 * solo_warps<L, R2>(), kPairMinBlocks) st_s
                         const float2 od = make_float2(zk.y + zp.y, zp.x - zk.x);
                         const float2 t = cmul(od, cm_.twp[k]);
                         const float ar = ev.x + t.x, ai = ev.y + t.y, br = ev.x - t.x, bi = ev.y - t.y;
-                        row[k] = fsqrt_fast(fmaf(ar, ar, ai * ai)) * scf;
-                        row[Nc - k] = fsqrt_fast(fmaf(br, br, bi * bi)) * scf;
+                        dst[k] = fsqrt_fast(fmaf(ar, ar, ai * ai)) * sc;
+                        dst[Nc - k] = fsqrt_fast(fmaf(br, br, bi * bi)) * sc;
                     }
                 }
                 if (lane == 0) {
                     const float2 z0 = wm.tz[0];
                     // DC: a sum(x - x0) + N (a (x0 - m) + bp), over K
-                    row[0] = fabsf(fmaf(nm.a, z0.x + z0.y, float(N) * fmaf(nm.a, u0 - cmv, nm.bp))) / float(K);
+                    dst[0] = fabsf(fmaf(nm.a, z0.x + z0.y, float(N) * fmaf(nm.a, u0 - cmv, nm.bp))) / float(K);
                     if ((Nc & 1) == 0) {
                         const float2 zm = wm.tz[Nc / 2];
-                        row[Nc / 2] = fsqrt_fast(fmaf(zm.x, zm.x, zm.y * zm.y)) * (2.f * scf);
+                        dst[Nc / 2] = fsqrt_fast(fmaf(zm.x, zm.x, zm.y * zm.y)) * (2.f * sc);
                     }
                 }
-                if (lane < Kp - K) row[K + lane] = 0.f;
-                if (Kp - K > 32 && lane + 32 < Kp - K) row[K + 32 + lane] = 0.f;
+                if (!gdst) {
+                    if (lane < Kp - K) row[K + lane] = 0.f;
+                    if (Kp - K > 32 && lane + 32 < Kp - K) row[K + 32 + lane] = 0.f;
+                }
+                __syncwarp();
+            };
+            if constexpr (MODE == kModeFeatures) {
+#pragma unroll 1
+                for (int f = 0; f < 2; ++f) {
+                    const int64_t s0 = f ? sb0 : sa0;
+                    const float u0 = is16 ? s16(s0) : s32(s0);
+                    float2 z[R2];
+                    load_points(s0, u0, z);
+                    transform(z, u0, f ? rowb : rowa, nullptr);
+                }
+            } else {
+                // row modes: few registers are busy, so the samples of both frames are fetched before the first transform starts;
+                // rows the reference's loop never reaches are zeros and touch no sample
+                float *const g0 = MODE == kModeSpectrogram ? p.out + (size_t(b) * p.rows_total + p.row0 + ta) * K : nullptr;
+                float2 za[R2], zb[R2];
+                float u0a = 0.f, u0b = 0.f;
+                const bool do_b = bvalid && b_real;
+                if (a_real) { u0a = is16 ? s16(sa0) : s32(sa0); load_points(sa0, u0a, za); }
+                if (do_b) { u0b = is16 ? s16(sb0) : s32(sb0); load_points(sb0, u0b, zb); }
+                if (a_real) transform(za, u0a, rowa, g0);
+                else if (MODE == kModeSpectrogram) { for (int k = lane; k < K; k += 32) g0[k] = 0.f; }
+                else { for (int k = lane; k < Kp; k += 32) rowa[k] = 0.f; }
+                if (do_b) transform(zb, u0b, rowb, g0 ? g0 + K : nullptr);
+                else if (MODE == kModeSpectrogram) { if (bvalid) for (int k = lane; k < K; k += 32) g0[K + k] = 0.f; }
+                else { for (int k = lane; k < Kp; k += 32) rowb[k] = 0.f; }
                 __syncwarp();
             }
 
             if constexpr (MODE == kModeSpectrogram) {
-                float *const dst = p.out + (size_t(b) * p.rows_total + p.row0 + ta) * K;
-                for (int k = lane; k < K; k += 32) {
-                    dst[k] = rowa[k];
-                    if (bvalid) dst[K + k] = rowb[k];
-                }
-                __syncwarp();
+                // rows went straight to global memory
             } else if constexpr (MODE == kModeChromagram) {
                 const float *X = half ? rowb : rowa;
                 float sxx = 0.f;

@@ -69,11 +69,23 @@ def main():
     ms_fe = timed(lambda: pkg.feature_extraction_batch(c3, 44100, w3, s3), reps=3)
     ms_sp = timed(lambda: pkg.spectrogram_batch(c3, 44100, w3, s3), reps=3)
     ms_ch = timed(lambda: pkg.chromagram_batch(c3, 44100, w3, s3), reps=3)
+    # the kernels alone (clip statistics computed once, outputs preallocated)
+    n3 = clip_stats(c3)
+    o_fe = torch.empty((B3, 68, T3), device="cuda")
+    o_sp = torch.empty((B3, T3, 441), device="cuda")
+    k_fe = timed(lambda: pkg.feature_extraction_batch(c3, 44100, w3, s3, norm=n3, out=o_fe), reps=5)
+    k_sp = timed(lambda: pkg.spectrogram_batch(c3, 44100, w3, s3, norm=n3, out=o_sp), reps=5)
+    k_ch = timed(lambda: pkg.chromagram_batch(c3, 44100, w3, s3, norm=n3), reps=5)
+    del o_fe, o_sp
     alg = B3 * (2 * N3 + 4 * (T3 * 441 + (T3 - 1) * 12 + 13 * T3))
     emit({"config": "3: %d x 60 s @44.1 kHz, 20/10 ms" % B3, "frames_per_clip": T3, "feature_extraction_ms": ms_fe, "spectrogram_ms": ms_sp,
           "chromagram_ms": ms_ch, "feature_extraction_frames_per_s": B3 * T3 / (ms_fe * 1e-3), "spectrogram_rows_per_s": B3 * T3 / (ms_sp * 1e-3),
           "chromagram_rows_per_s": B3 * T3 / (ms_ch * 1e-3), "spectrogram_GBps": B3 * (2 * N3 + 4 * T3 * 441) / (ms_sp * 1e-3) / 1e9,
           "spectrogram_frac_of_hbm_peak": B3 * (2 * N3 + 4 * T3 * 441) / (ms_sp * 1e-3) / 1e9 / PEAK,
+          "kernel_only_ms": {"feature_extraction": k_fe, "spectrogram": k_sp, "chromagram": k_ch},
+          "kernel_only_spectrogram_GBps": B3 * (2 * N3 + 4 * T3 * 441) / (k_sp * 1e-3) / 1e9,
+          "kernel_only_spectrogram_frac_of_hbm_peak": B3 * (2 * N3 + 4 * T3 * 441) / (k_sp * 1e-3) / 1e9 / PEAK,
+          "kernel_only_feature_extraction_frames_per_s": B3 * T3 / (k_fe * 1e-3),
           "combined_algorithmic_GBps": alg / ((ms_sp + ms_ch + ms_fe) * 1e-3) / 1e9, "hbm_peak_GBps": PEAK})
     del c3
 
