@@ -108,11 +108,11 @@ def main():
     # ---- other windows on the config-2 batch, per kernel kind
     cg = noise(1000, 160000, 5)
     norm = clip_stats(cg)
-    for w, s in ((800, 400), (1024, 512), (512, 256), (640, 320), (960, 480), (480, 240), (320, 160), (400, 160), (2048, 1024)):
+    for w, s in ((800, 400), (1024, 512), (512, 256), (640, 320), (960, 480), (480, 240), (320, 160), (400, 160), (600, 300), (2048, 1024)):
         T = (160000 - w) // s + 1
         out = torch.empty((1000, 68, T), device="cuda")
         row = {"config": "other windows: 1000 x 10 s @16 kHz", "window": w, "step": s, "frames": 1000 * T}
-        for kind in (2, 1, 0):
+        for kind in (2, 3, 1, 0):
             pl = Plan(16000, w, s).prefer_kernel(kind)
             if pl.kernel_kind() != kind:
                 continue
