@@ -79,6 +79,21 @@ def test_float_input_odd_window(P, golden_synth):
     check_features(F, golden_synth["st_float_551"], 275, "float64 input, window 551, step 200, no deltas")
 
 
+def test_other_sample_formats(P):
+    """Integer formats other than int16: 8-bit and unsigned 16-bit PCM are exact in the device formats; 32-bit PCM (as
+    scipy returns 24 / 32-bit WAV files) goes through float32 -- the path is scale invariant and the 2^-24 relative
+    rounding of a sample is far below the tolerance."""
+    rng = np.random.default_rng(17)
+    base = O.synth_clip(91, 24000, 16000)
+    x32 = base.astype(np.int32) * 65536 + rng.integers(-30000, 30000, base.shape[0])          # 32-bit PCM with live low bits
+    x24 = (base.astype(np.int32) * 256 + rng.integers(-100, 100, base.shape[0])).astype(np.int32)
+    u8 = ((base // 256) + 128).astype(np.uint8)
+    u16 = (base.astype(np.int32) + 32768).astype(np.uint16)
+    for name, x in (("int32", x32), ("24-bit in int32", x24), ("uint8", u8), ("uint16", u16), ("float64", base.astype(np.float64) / 32768.0)):
+        F, _ = P.ShortTermFeatures.feature_extraction(x, 16000, 800, 400)
+        check_features(F, O.feature_extraction(x, 16000, 800, 400)[0], 400, "input format " + name)
+
+
 def test_one_second_windows(P, golden_synth):
     """music_thumbnailing calls the path with 1 s windows (audioSegmentation.py:1137-1139)."""
     F, _ = P.ShortTermFeatures.feature_extraction(O.synth_clip(13, 80000, 16000), 16000, 16000, 16000)
