@@ -41,21 +41,53 @@ struct alignas(16) SoloWarpMem {
     float blk[24];                           // block energies: a -> [0, 10), b -> [10, 20), rests at 20, 21
 };
 
-template <int L, int R2>
+// the row modes (spectrogram / chromagram) keep only the transform buffer and the two |X| rows: small CTAs, more of them per SM
+// (the spectrogram stores its rows straight to global memory and keeps the transform buffer only)
+template <int L, int R2, int MODE>
+struct alignas(16) SoloRowWarpMem {
+    using S = SoloShape<L, R2>;
+    float2 tz[S::TZ];
+    alignas(16) float rows[2][MODE == kModeChromagram ? S::Kp : 4];
+};
+template <int L, int R2, int MODE> struct SoloWarpMemFor { using type = SoloRowWarpMem<L, R2, MODE>; };
+template <int L, int R2> struct SoloWarpMemFor<L, R2, kModeFeatures> { using type = SoloWarpMem<L, R2>; };
+
+// Measured on config 3 (64 x 60 s @44.1 kHz), warps per CTA x CTAs per SM -> spectrogram / chromagram ms:
+//   8 x 2 (126 regs, the feature layout) 0.558 / 0.592    5 x 4 (96 regs) 0.543 / 0.558    8 x 3 (80 regs) 0.502 / 0.537
+//   6 x 4 (80) 0.499 / 0.546    7 x 4 (71) 0.490 / 0.561    10 x 3 (64) 0.485 / 0.565    8 x 4 (64 regs, 32 warps) 0.478 / 0.552
+// (the chromagram's two |X| rows per warp cap it at 3 CTAs of 8 warps)
+#ifndef B200AA_SOLO_ROW_WARPS
+#define B200AA_SOLO_ROW_WARPS 8
+#endif
+#ifndef B200AA_SOLO_SPEC_BLOCKS
+#define B200AA_SOLO_SPEC_BLOCKS 4
+#endif
+#ifndef B200AA_SOLO_CHROMA_BLOCKS
+#define B200AA_SOLO_CHROMA_BLOCKS 3
+#endif
+constexpr int kSoloRowWarps = B200AA_SOLO_ROW_WARPS;
+
+template <int L, int R2, int MODE = kModeFeatures>
 __host__ __device__ constexpr int solo_warps()
 {
+    if (MODE != kModeFeatures) return kSoloRowWarps;
     constexpr int budget = 113 * 1024 - (L * R2 + L * R2 / 2 + 2) * 8 - 256 - 6656;
     constexpr int w = budget / int(sizeof(SoloWarpMem<L, R2>));
     return w > kPairMaxWarps ? kPairMaxWarps : (w < 2 ? 2 : w);
 }
+template <int MODE>
+__host__ __device__ constexpr int solo_min_blocks()
+{
+    return MODE == kModeFeatures ? kPairMinBlocks : (MODE == kModeSpectrogram ? B200AA_SOLO_SPEC_BLOCKS : B200AA_SOLO_CHROMA_BLOCKS);
+}
 
-template <int L, int R2>
+template <int L, int R2, int MODE = kModeFeatures>
 struct alignas(16) SoloCtaMem {
     using S = SoloShape<L, R2>;
     float2 tw[R2 * L];                       // W_Nc^(k1 n2), [k1][n2]
     float2 twp[(S::Nc / 2 + 2) & ~1];        // W_N^k, k <= Nc / 2
     alignas(16) int dlane[16 * 4];
-    SoloWarpMem<L, R2> w[solo_warps<L, R2>()];
+    typename SoloWarpMemFor<L, R2, MODE>::type w[solo_warps<L, R2, MODE>()];
 };
 
 struct SoloParams {
@@ -67,8 +99,11 @@ struct SoloParams {
     int seg_big, n_big, seg_small, segs_per_clip;       // runs of pairs per clip (as in the pair kernel)
 };
 
-template <int L, int R2>
-inline size_t solo_smem_bytes(int blob_words) { return sizeof(SoloCtaMem<L, R2>) + sizeof(int) * size_t((blob_words + 3) & ~3); }
+template <int L, int R2, int MODE = kModeFeatures>
+inline size_t solo_smem_bytes(int blob_words)
+{
+    return sizeof(SoloCtaMem<L, R2, MODE>) + (MODE == kModeSpectrogram ? 0 : sizeof(int) * size_t((blob_words + 3) & ~3));   // no tables
+}
 
 // time-domain accumulation of BOTH frames over all rows (u[r] = (sample of a, sample of b) of lane l = sample 32 r + l);
 // see td_pair in pair_kernel.cuh -- this form takes any window length (the last row is partial)
@@ -116,17 +151,18 @@ __device__ __forceinline__ void td_rows(const float2 (&u)[SoloShape<L, R2>::RT],
 }
 
 template <int L, int R2, int MODE>
-__global__ void __launch_bounds__(32 * solo_warps<L, R2>(), kPairMinBlocks) st_solo_kernel(const SoloParams pp)
+__global__ void __launch_bounds__(32 * solo_warps<L, R2, MODE>(), solo_min_blocks<MODE>()) st_solo_kernel(const SoloParams pp)
 {
     using S = SoloShape<L, R2>;
     constexpr int Nc = S::Nc, N = S::N, K = S::K, Kp = S::Kp, RT = S::RT, TS = S::TS, KH = S::KH;
-    constexpr int NTHR = 32 * solo_warps<L, R2>();
+    constexpr int NTHR = 32 * solo_warps<L, R2, MODE>();
+    constexpr bool FEAT = MODE == kModeFeatures;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SoloCtaMem<L, R2> &cm_ = *reinterpret_cast<SoloCtaMem<L, R2> *>(smem_raw);
-    int *const blob_s = reinterpret_cast<int *>(smem_raw + sizeof(SoloCtaMem<L, R2>));
+    SoloCtaMem<L, R2, MODE> &cm_ = *reinterpret_cast<SoloCtaMem<L, R2, MODE> *>(smem_raw);
+    int *const blob_s = reinterpret_cast<int *>(smem_raw + sizeof(SoloCtaMem<L, R2, MODE>));
     const StParams &p = pp.st;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < pp.pbl.words; i += NTHR) blob_s[i] = pp.pblob[i];
+    if constexpr (MODE != kModeSpectrogram) { for (int i = tid; i < pp.pbl.words; i += NTHR) blob_s[i] = pp.pblob[i]; }
     for (int i = tid; i < R2 * L; i += NTHR) cm_.tw[i] = pp.tw[i];
     for (int i = tid; i < Nc / 2 + 1; i += NTHR) cm_.twp[i] = pp.twp[i];
     if (tid < 16) *reinterpret_cast<int4 *>(cm_.dlane + tid * 4) = pair_lane_init<K>(tid);
@@ -134,8 +170,7 @@ __global__ void __launch_bounds__(32 * solo_warps<L, R2>(), kPairMinBlocks) st_s
     const FeatTables ftab{reinterpret_cast<const float *>(blob_s + pp.pbl.dct), blob_s + pp.pbl.mel_rec,
                           reinterpret_cast<const float4 *>(blob_s + pp.pbl.mel_w), reinterpret_cast<const int2 *>(blob_s + pp.pbl.chr),
                           pp.pbl.lq, pp.pbl.ct};
-    SoloWarpMem<L, R2> &wm = cm_.w[warp];
-    float *const msraw = wm.mel, *const mslog = msraw + 2 * B200AA_N_MEL, *const mfold = mslog + 2 * B200AA_N_MEL;
+    auto &wm = cm_.w[warp];
     const int step = p.step;
     const int half = lane >> 4, l16 = lane & 15;
     const unsigned FULLM = 0xffffffffu;
@@ -181,10 +216,9 @@ __global__ void __launch_bounds__(32 * solo_warps<L, R2>(), kPairMinBlocks) st_s
             const bool bvalid = ta + 1 < T;
             const int tbb = bvalid ? ta + 1 : ta;
             const int64_t sa0 = origin + int64_t(ta) * step, sb0 = origin + int64_t(tbb) * step;       // first samples
-            const int ia = sa % 3, ib = (sa + 1) % 3, ip = (sa + 2) % 3;
+            const int ia = FEAT ? sa % 3 : 0, ib = FEAT ? (sa + 1) % 3 : 1, ip = (sa + 2) % 3;
             float *const rowa = wm.rows[ia], *const rowb = wm.rows[ib];
             const int ra = store ? 1 + tile_n : 8, rb = store ? 2 + tile_n : 0;
-            float *const fva = wm.fv + ra * kFvStride, *const fvb = wm.fv + rb * kFvStride;
             const bool a_real = MODE == kModeFeatures || ta < n_valid, b_real = MODE == kModeFeatures || tbb < n_valid;
 
             // ---- time-domain rows (features only): whole frames in the row layout
@@ -230,7 +264,7 @@ __global__ void __launch_bounds__(32 * solo_warps<L, R2>(), kPairMinBlocks) st_s
                 const float sj = fdiv(e, tot + B200AA_EPS);
                 const float H = half_sum(own ? -sj * flog2(sj + B200AA_EPS) : 0.f);
                 if (l16 == 0) {
-                    float *fv = half ? fvb : fva;
+                    float *fv = wm.fv + (half ? rb : ra) * kFvStride;
                     fv[0] = float(half ? fl_b : fl_a) * 0.5f / float(N - 1);
                     fv[1] = tot / float(N);
                     fv[2] = H;
@@ -279,7 +313,7 @@ __global__ void __launch_bounds__(32 * solo_warps<L, R2>(), kPairMinBlocks) st_s
                 }
                 __syncwarp();
                 // post-processing: (Z[k], Z[Nc-k]) -> |X[k]|, |X[Nc-k]|  (X = ev + W_N^k od, X' = conj(ev - W_N^k od))
-                float *const dst = gdst ? gdst : row;
+                float *const dst = MODE == kModeSpectrogram ? gdst : row;
 #pragma unroll
                 for (int j = 0; j < (KH + 31) / 32; ++j) {
                     const int k = 1 + lane + 32 * j;
@@ -302,7 +336,7 @@ __global__ void __launch_bounds__(32 * solo_warps<L, R2>(), kPairMinBlocks) st_s
                         dst[Nc / 2] = fsqrt_fast(fmaf(zm.x, zm.x, zm.y * zm.y)) * (2.f * sc);
                     }
                 }
-                if (!gdst) {
+                if constexpr (MODE != kModeSpectrogram) {
                     if (lane < Kp - K) row[K + lane] = 0.f;
                     if (Kp - K > 32 && lane + 32 < Kp - K) row[K + 32 + lane] = 0.f;
                 }
@@ -327,7 +361,7 @@ __global__ void __launch_bounds__(32 * solo_warps<L, R2>(), kPairMinBlocks) st_s
                     float *const gd = g0 ? g0 + f * K : nullptr;
                     float *const row = f ? rowb : rowa;
                     if (!(f ? b_real : a_real)) {
-                        if (gd) { for (int k = lane; k < K; k += 32) gd[k] = 0.f; }
+                        if constexpr (MODE == kModeSpectrogram) { for (int k = lane; k < K; k += 32) gd[k] = 0.f; }
                         else { for (int k = lane; k < Kp; k += 32) row[k] = 0.f; }
                         continue;
                     }
@@ -359,8 +393,9 @@ __global__ void __launch_bounds__(32 * solo_warps<L, R2>(), kPairMinBlocks) st_s
                     p.out[(size_t(b) * p.rows_total + p.row0 + ta + half) * 12 + l16] = (half ? b_real : a_real) ? ch : 0.f;
                 __syncwarp();
             } else {
+                float *const msraw = wm.mel, *const mslog = msraw + 2 * B200AA_N_MEL, *const mfold = mslog + 2 * B200AA_N_MEL;
                 rows_to_features<K>(rowa, rowb, fresh ? rowa : wm.rows[ip], fresh, wm.fv[(ra - 1) * kFvStride + 34], cm_.dlane,
-                                    wm.parts, msraw, mslog, mfold, wm.chr, fva, fvb, ftab, lane);
+                                    wm.parts, msraw, mslog, mfold, wm.chr, wm.fv + ra * kFvStride, wm.fv + rb * kFvStride, ftab, lane);
                 if (store) {
                     tile_n += bvalid ? 2 : 1;
                     if (tile_n == 8 || q == q1 - 1) {
@@ -440,12 +475,12 @@ inline int solo_plan_init(int window, const std::vector<int> &h_pblob, const Pai
 template <int L, int R2, int MODE>
 inline int solo_launch_t(const SoloTables &stb, const StParams &p, int sm_count, int64_t T, unsigned int *counter, cudaStream_t st)
 {
-    const size_t smem = solo_smem_bytes<L, R2>(stb.pbl.words);
+    const size_t smem = solo_smem_bytes<L, R2, MODE>(stb.pbl.words);
     if (smem > 113u * 1024u) return B200AA_ERR_UNSUPPORTED;
     auto kern = st_solo_kernel<L, R2, MODE>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024) != cudaSuccess) return B200AA_ERR_CUDA;
     int occ = 1;
-    constexpr int W = solo_warps<L, R2>();
+    constexpr int W = solo_warps<L, R2, MODE>();
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W, smem) != cudaSuccess) return B200AA_ERR_CUDA;
     occ = occ < 1 ? 1 : occ;
     SoloParams pp;
