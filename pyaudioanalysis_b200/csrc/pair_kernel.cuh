@@ -28,11 +28,30 @@
 
 namespace b200aa {
 
+// Resident warps per SM.  Measured on B200 (1000 x 10 s @16 kHz, 800 / 400; profiles/ab_diet_r2.jsonl), CTAs x warps:
+//   2 x 8 at 128 registers (round 2's first layout, 11.9 KB of shared memory per warp) 0.904 ms;  the 9.6 KB layout below:
+//   2 x 8 (128 regs) 0.916   2 x 10 (96 regs; 3+3+2+2 warps per scheduler and CTA) 0.923   1 x 22 (80 regs, spills) 0.874
+//   1 x 20 (96 regs, five warps per scheduler) 0.824  <- what the 800-sample window gets (22 warps would fit).  Warps per CTA
+//   stay a multiple of four: a CTA's warps go round-robin to the four schedulers of the SM.  The shorter windows fit 24 warps
+//   (80 registers, no spills to speak of): 640 / 320 0.868 -> 0.851 ms, 512 / 256 1.024 -> 0.984, 320 / 160 1.236 -> 1.191
+//   (profiles/ab_solo_r2.jsonl); 960 and 1024 samples run 16 warps at 128 registers.
 #ifndef B200AA_PAIR_MAXWARPS
-#define B200AA_PAIR_MAXWARPS 8
+#define B200AA_PAIR_MAXWARPS 24
 #endif
 constexpr int kPairMaxWarps = B200AA_PAIR_MAXWARPS;     // warps per CTA (each one autonomous); fewer for the longest windows (shared memory)
-constexpr int kPairMinBlocks = 2;    // 2 CTAs per SM: 16 warps at <= 128 registers
+#ifndef B200AA_PAIR_MINBLOCKS
+#define B200AA_PAIR_MINBLOCKS 1
+#endif
+constexpr int kPairMinBlocks = B200AA_PAIR_MINBLOCKS;   // one CTA per SM: the twiddle / mel / DCT / chroma tables exist once per SM
+// the solo kernel's feature layout (solo_kernel.cuh): config 3 (64 x 60 s @44.1 kHz, 882 / 441) 2 x 8 warps 1.162 ms, 1 x 20 1.067,
+// 1 x 24 (80 registers, no spills) 1.075; 400 / 160 on the bench batch 1.808 / 1.625 / 1.599
+#ifndef B200AA_SOLO_MAXWARPS
+#define B200AA_SOLO_MAXWARPS 24
+#endif
+#ifndef B200AA_SOLO_MINBLOCKS
+#define B200AA_SOLO_MINBLOCKS 1
+#endif
+constexpr int kSoloMaxWarps = B200AA_SOLO_MAXWARPS, kSoloMinBlocks = B200AA_SOLO_MINBLOCKS;
 
 template <int R>
 struct PairShape {
@@ -45,30 +64,38 @@ struct PairShape {
     static constexpr bool kShareable = (N % 160) == 0;    // half a frame = 5 whole blocks, rows split at lane 0 / 16 only
     // after the separation the transform buffer holds the |X| row of frame a (Kp floats) and, behind it, the mel scratch:
     // filter outputs, their log10, and the folded halves for the DCT ([f][0..19] sums, [f][20..39] differences), 2 x 40 each
+    // (everything one step needs between the separation and the next transform lives in the transform buffer: a warp keeps
+    // only the previous pair's |X| row, the feature tile and the block-energy ring beside it -- 9.6 KB for the 800-sample
+    // window instead of 11.9 KB, i.e. 20-22 resident warps per SM instead of 16)
     static constexpr int MS0 = (Kp + 3) & ~3;
-    static_assert(2 * TZ >= MS0 + 6 * B200AA_N_MEL, "|X| row of frame a + mel scratch fit the transform buffer");
+    static constexpr int RB0 = MS0 + 6 * B200AA_N_MEL;       // |X| row of frame b (Kp floats, 16-byte aligned)
+    static constexpr int PT0 = RB0 + Kp;                     // spectral-entropy parts of the dense pass (2 x 32)
+    static constexpr int CH0 = PT0 + 64;                     // raw chroma sums (2 x 12)
+    static_assert(2 * TZ >= CH0 + 24, "|X| rows of both frames + mel scratch + parts + chroma fit the transform buffer");
+    static_assert((RB0 % 4) == 0, "aligned |X| row");
     static_assert(Lt >= 32, "a 32-sample row touches two blocks at most");
 };
 
 template <int R>
 struct alignas(16) PairWarpMem {
     using S = PairShape<R>;
-    float2 tz[S::TZ];                       // pass-1 outputs, planes re[k1][LS] | im[k1][LS]  ->  Z[k] (natural order, Z[N] = Z[0])  ->  |X| row of a
-    alignas(16) float rowb[2][S::Kp];       // |X| rows of frame b: this step's and the previous step's (alternating)
+    float2 tz[S::TZ];                       // pass-1 outputs, planes re[k1][LS] | im[k1][LS]  ->  Z[k] (natural order, Z[N] = Z[0])  ->
+                                            // |X| row of a | mel scratch | |X| row of b | entropy parts | chroma sums (PairShape::MS0 ...)
+    alignas(16) float rowp[S::Kp];          // |X| row of the previous pair's frame b (the flux of frame a needs it)
     float fv[9 * kFvStride];                // feature rows: row 0 = the frame before the tile, rows 1..8 = the tile
-    float chr[2 * 12];                      // raw chroma sums
-    float parts[2 * 32];                    // spectral-entropy parts of the dense pass
     float blk[24];                          // block energies: a -> [0, 10), b -> [5, 15) (shared halves) or [10, 20); rests at 20, 21
 };
 
-// warps per CTA such that two CTAs fit the 227 KB of an SM (per CTA: 113 KB cap of pair_launch_t, twiddles, lane
+// warps per CTA such that kPairMinBlocks CTAs fit the 227 KB of an SM (per CTA: kPairCtaCap of pair_launch_t, twiddles, lane
 // constants, up to 6.5 KB of mel / DCT / chroma tables)
+constexpr int kPairCtaCap = (kPairMinBlocks == 1 ? 227 : (kPairMinBlocks == 2 ? 113 : 228 / kPairMinBlocks - 1)) * 1024;
 template <int R>
 __host__ __device__ constexpr int pair_warps()
 {
-    constexpr int budget = 113 * 1024 - R * 32 * 8 - 256 - 6656;
+    constexpr int budget = kPairCtaCap - R * 32 * 8 - 256 - 6656;
     constexpr int w = budget / int(sizeof(PairWarpMem<R>));
-    return w > kPairMaxWarps ? kPairMaxWarps : (w < 2 ? 2 : w);
+    constexpr int c = w > kPairMaxWarps ? kPairMaxWarps : (w < 2 ? 2 : w);
+    return c >= 4 ? (c & ~3) : c;           // whole rounds over the four schedulers
 }
 
 template <int R>
@@ -572,7 +599,6 @@ __global__ void __launch_bounds__(32 * pair_warps<R>(), kPairMinBlocks) st_pair_
         const float fscale = nm.a * (0.5f / float(K));
 
         bool fresh = true;          // no state carried from a previous pair (first step of the item)
-        int cur = 0;                // rowb[cur] receives this step's frame b; rowb[cur ^ 1] holds the previous one
         int tile_n = 0, tile_t0 = 2 * q0;
         int zprev = 0;              // sign flips inside the first half of frame a (= second half of the previous b)
         // samples: lane l holds samples 32 r + l of both frames of a pair, as exact floats M0 + x.
@@ -775,7 +801,7 @@ __global__ void __launch_bounds__(32 * pair_warps<R>(), kPairMinBlocks) st_pair_
                 }
             }
             __syncwarp();                    // every lane has read Z: the buffer becomes the |X| row of frame a
-            float *const rowbn = wm.rowb[cur];
+            float *const rowbn = rowa + S::RB0;
 #pragma unroll
             for (int j = 0; j < C; ++j) { rowa[lane + 32 * j] = xa[j]; rowbn[lane + 32 * j] = xb[j]; }
             if (pp.dbg) {
@@ -790,8 +816,11 @@ __global__ void __launch_bounds__(32 * pair_warps<R>(), kPairMinBlocks) st_pair_
             }
             __syncwarp();
             // ---- spectral rows, mel / chroma / DCT: half-warp per frame over the two |X| rows
-            rows_to_features<K>(rowa, rowbn, fresh ? rowa : wm.rowb[cur ^ 1], fresh, wm.fv[(ra - 1) * kFvStride + 34], cm_.dlane,
-                                wm.parts, msraw, mslog, mfold, wm.chr, fva, fvb, ftab, lane);
+            rows_to_features<K>(rowa, rowbn, fresh ? rowa : wm.rowp, fresh, wm.fv[(ra - 1) * kFvStride + 34], cm_.dlane,
+                                rowa + S::PT0, msraw, mslog, mfold, rowa + S::CH0, fva, fvb, ftab, lane);
+            // frame b's row outlives the next transform beside the buffer (rows_to_features ends with a __syncwarp)
+#pragma unroll
+            for (int j = 0; j < C; ++j) wm.rowp[lane + 32 * j] = rowbn[lane + 32 * j];
 
             // ---- tile bookkeeping / store
             if (store) {
@@ -807,7 +836,7 @@ __global__ void __launch_bounds__(32 * pair_warps<R>(), kPairMinBlocks) st_pair_
                 }
             }
             fresh = false;
-            cur ^= 1;
+            __syncwarp();                    // the copy above has read the buffer before the next step's pass 1 overwrites it
         }
     }
 }
@@ -950,10 +979,10 @@ inline int pair_launch_t(const PairTables &pt, const StParams &p, int sm_count, 
                          cudaStream_t st)
 {
     const size_t smem = pair_smem_bytes<R>(pt.pbl.words);
-    if (smem > 113u * 1024u) return B200AA_ERR_UNSUPPORTED;
+    if (smem > size_t(kPairCtaCap)) return B200AA_ERR_UNSUPPORTED;
     auto kern = st_pair_kernel<R, SHARED>;
     // always the cap, so concurrent launches of one instantiation cannot undercut each other
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024) != cudaSuccess) return B200AA_ERR_CUDA;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairCtaCap) != cudaSuccess) return B200AA_ERR_CUDA;
     int occ = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * pair_warps<R>(), smem) != cudaSuccess) return B200AA_ERR_CUDA;
     occ = occ < 1 ? 1 : occ;

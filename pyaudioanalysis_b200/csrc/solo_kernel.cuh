@@ -24,7 +24,11 @@ struct SoloShape {
     static constexpr int Lt = N / 10;
     static constexpr int NREST = (N % 10) ? 1 : 0, NE = 10 + NREST;
     static constexpr int KH = (Nc - 1) / 2;              // pairs (k, Nc - k), k = 1 .. KH; Nc even: bin Nc / 2 pairs with itself
+    // feature layout: after frame b's transform its |X| row, the mel scratch, the entropy parts and the chroma sums live in the
+    // transform buffer (floats): a warp keeps only frame a's row, the previous b row, the feature tile and the block energies beside it
     static constexpr int MS0 = (Kp + 3) & ~3;
+    static constexpr int PT0 = MS0 + 6 * B200AA_N_MEL, CH0 = PT0 + 64;
+    static constexpr int TZF = (2 * TZ >= CH0 + 24) ? TZ : (CH0 + 24 + 1) / 2;      // float2 elements of the feature layout's buffer
     static_assert(L <= 32 && R2 <= 32, "one lane per column / row");
     static_assert(Lt >= 32 && (Lt % 2) == 0, "a 32-sample row touches two energy blocks at most");
 };
@@ -32,12 +36,10 @@ struct SoloShape {
 template <int L, int R2>
 struct alignas(16) SoloWarpMem {
     using S = SoloShape<L, R2>;
-    float2 tz[S::TZ];                        // pass-1 outputs [k1][TS]  ->  Z[k] (natural order)
-    alignas(16) float rows[3][S::Kp];        // |X| rows: frame a, frame b, and the previous step's b (rotating)
+    float2 tz[S::TZF];                       // pass-1 outputs [k1][TS]  ->  Z[k] (natural order)  ->  (after frame b) |X| row of b | mel scratch | parts | chroma
+    alignas(16) float rowa[S::Kp];           // |X| row of frame a
+    alignas(16) float rowp[S::Kp];           // |X| row of the previous step's frame b
     float fv[9 * kFvStride];
-    float mel[6 * B200AA_N_MEL];             // filter outputs, their log10, folded halves
-    float chr[2 * 12];
-    float parts[2 * 32];
     float blk[24];                           // block energies: a -> [0, 10), b -> [10, 20), rests at 20, 21
 };
 
@@ -66,19 +68,21 @@ template <int L, int R2> struct SoloWarpMemFor<L, R2, kModeFeatures> { using typ
 #define B200AA_SOLO_CHROMA_BLOCKS 3
 #endif
 constexpr int kSoloRowWarps = B200AA_SOLO_ROW_WARPS;
+constexpr int kSoloCtaCap = (kSoloMinBlocks == 1 ? 227 : (kSoloMinBlocks == 2 ? 113 : 228 / kSoloMinBlocks - 1)) * 1024;   // feature layout
 
 template <int L, int R2, int MODE = kModeFeatures>
 __host__ __device__ constexpr int solo_warps()
 {
     if (MODE != kModeFeatures) return kSoloRowWarps;
-    constexpr int budget = 113 * 1024 - (L * R2 + L * R2 / 2 + 2) * 8 - 256 - 6656;
+    constexpr int budget = kSoloCtaCap - (L * R2 + L * R2 / 2 + 2) * 8 - 256 - 6656;
     constexpr int w = budget / int(sizeof(SoloWarpMem<L, R2>));
-    return w > kPairMaxWarps ? kPairMaxWarps : (w < 2 ? 2 : w);
+    constexpr int c = w > kSoloMaxWarps ? kSoloMaxWarps : (w < 2 ? 2 : w);
+    return c >= 4 ? (c & ~3) : c;            // whole rounds over the four schedulers
 }
 template <int MODE>
 __host__ __device__ constexpr int solo_min_blocks()
 {
-    return MODE == kModeFeatures ? kPairMinBlocks : (MODE == kModeSpectrogram ? B200AA_SOLO_SPEC_BLOCKS : B200AA_SOLO_CHROMA_BLOCKS);
+    return MODE == kModeFeatures ? kSoloMinBlocks : (MODE == kModeSpectrogram ? B200AA_SOLO_SPEC_BLOCKS : B200AA_SOLO_CHROMA_BLOCKS);
 }
 
 template <int L, int R2, int MODE = kModeFeatures>
@@ -208,7 +212,6 @@ __global__ void __launch_bounds__(32 * solo_warps<L, R2, MODE>(), solo_min_block
 
         bool fresh = true;
         int tile_n = 0, tile_t0 = 2 * q0;
-        int sa = 0;                 // rows[sa] = frame a, rows[sa + 1] = frame b, rows[sa + 2] = previous b (indices mod 3)
         const int halo = (MODE == kModeFeatures && q0 > 0) ? 1 : 0;
         for (int q = q0 - halo; q < q1; ++q) {
             const bool store = q >= q0;
@@ -216,8 +219,9 @@ __global__ void __launch_bounds__(32 * solo_warps<L, R2, MODE>(), solo_min_block
             const bool bvalid = ta + 1 < T;
             const int tbb = bvalid ? ta + 1 : ta;
             const int64_t sa0 = origin + int64_t(ta) * step, sb0 = origin + int64_t(tbb) * step;       // first samples
-            const int ia = FEAT ? sa % 3 : 0, ib = FEAT ? (sa + 1) % 3 : 1, ip = (sa + 2) % 3;
-            float *const rowa = wm.rows[ia], *const rowb = wm.rows[ib];
+            float *rowa, *rowb;              // features: frame b's row lands in the transform buffer once its transform is done
+            if constexpr (FEAT) { rowa = wm.rowa; rowb = reinterpret_cast<float *>(wm.tz); }
+            else { rowa = wm.rows[0]; rowb = wm.rows[1]; }
             const int ra = store ? 1 + tile_n : 8, rb = store ? 2 + tile_n : 0;
             const bool a_real = MODE == kModeFeatures || ta < n_valid, b_real = MODE == kModeFeatures || tbb < n_valid;
 
@@ -314,27 +318,45 @@ __global__ void __launch_bounds__(32 * solo_warps<L, R2, MODE>(), solo_min_block
                 __syncwarp();
                 // post-processing: (Z[k], Z[Nc-k]) -> |X[k]|, |X[Nc-k]|  (X = ev + W_N^k od, X' = conj(ev - W_N^k od))
                 float *const dst = MODE == kModeSpectrogram ? gdst : row;
+                constexpr int NJ = (KH + 31) / 32;
+                float vlo[NJ], vhi[NJ];
 #pragma unroll
-                for (int j = 0; j < (KH + 31) / 32; ++j) {
+                for (int j = 0; j < NJ; ++j) {
                     const int k = 1 + lane + 32 * j;
+                    vlo[j] = 0.f; vhi[j] = 0.f;
                     if (k <= KH) {
                         const float2 zk = wm.tz[k], zp = wm.tz[Nc - k];
                         const float2 ev = make_float2(zk.x + zp.x, zk.y - zp.y);
                         const float2 od = make_float2(zk.y + zp.y, zp.x - zk.x);
                         const float2 t = cmul(od, cm_.twp[k]);
                         const float ar = ev.x + t.x, ai = ev.y + t.y, br = ev.x - t.x, bi = ev.y - t.y;
-                        dst[k] = fsqrt_fast(fmaf(ar, ar, ai * ai)) * sc;
-                        dst[Nc - k] = fsqrt_fast(fmaf(br, br, bi * bi)) * sc;
+                        vlo[j] = fsqrt_fast(fmaf(ar, ar, ai * ai)) * sc;
+                        vhi[j] = fsqrt_fast(fmaf(br, br, bi * bi)) * sc;
+                        if constexpr (!FEAT) { dst[k] = vlo[j]; dst[Nc - k] = vhi[j]; }
                     }
                 }
+                float dc = 0.f, mid = 0.f;
                 if (lane == 0) {
                     const float2 z0 = wm.tz[0];
                     // DC: a sum(x - x0) + N (a (x0 - m) + bp), over K
-                    dst[0] = fabsf(fmaf(nm.a, z0.x + z0.y, float(N) * fmaf(nm.a, u0 - cmv, nm.bp))) / float(K);
+                    dc = fabsf(fmaf(nm.a, z0.x + z0.y, float(N) * fmaf(nm.a, u0 - cmv, nm.bp))) / float(K);
                     if ((Nc & 1) == 0) {
                         const float2 zm = wm.tz[Nc / 2];
-                        dst[Nc / 2] = fsqrt_fast(fmaf(zm.x, zm.x, zm.y * zm.y)) * (2.f * sc);
+                        mid = fsqrt_fast(fmaf(zm.x, zm.x, zm.y * zm.y)) * (2.f * sc);
                     }
+                }
+                if constexpr (FEAT) {
+                    // the row may be the transform buffer itself (frame b): every lane has read Z before anybody writes
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        const int k = 1 + lane + 32 * j;
+                        if (k <= KH) { dst[k] = vlo[j]; dst[Nc - k] = vhi[j]; }
+                    }
+                }
+                if (lane == 0) {
+                    dst[0] = dc;
+                    if ((Nc & 1) == 0) dst[Nc / 2] = mid;
                 }
                 if constexpr (MODE != kModeSpectrogram) {
                     if (lane < Kp - K) row[K + lane] = 0.f;
@@ -393,9 +415,12 @@ __global__ void __launch_bounds__(32 * solo_warps<L, R2, MODE>(), solo_min_block
                     p.out[(size_t(b) * p.rows_total + p.row0 + ta + half) * 12 + l16] = (half ? b_real : a_real) ? ch : 0.f;
                 __syncwarp();
             } else {
-                float *const msraw = wm.mel, *const mslog = msraw + 2 * B200AA_N_MEL, *const mfold = mslog + 2 * B200AA_N_MEL;
-                rows_to_features<K>(rowa, rowb, fresh ? rowa : wm.rows[ip], fresh, wm.fv[(ra - 1) * kFvStride + 34], cm_.dlane,
-                                    wm.parts, msraw, mslog, mfold, wm.chr, wm.fv + ra * kFvStride, wm.fv + rb * kFvStride, ftab, lane);
+                float *const msraw = rowb + S::MS0, *const mslog = msraw + 2 * B200AA_N_MEL, *const mfold = mslog + 2 * B200AA_N_MEL;
+                rows_to_features<K>(rowa, rowb, fresh ? rowa : wm.rowp, fresh, wm.fv[(ra - 1) * kFvStride + 34], cm_.dlane,
+                                    rowb + S::PT0, msraw, mslog, mfold, rowb + S::CH0, wm.fv + ra * kFvStride, wm.fv + rb * kFvStride, ftab, lane);
+                // frame b's row outlives the next transforms beside the buffer (rows_to_features ends with a __syncwarp)
+#pragma unroll
+                for (int j = 0; j < Kp / 32; ++j) wm.rowp[lane + 32 * j] = rowb[lane + 32 * j];
                 if (store) {
                     tile_n += bvalid ? 2 : 1;
                     if (tile_n == 8 || q == q1 - 1) {
@@ -410,7 +435,7 @@ __global__ void __launch_bounds__(32 * solo_warps<L, R2, MODE>(), solo_min_block
                 }
             }
             fresh = false;
-            sa = (sa + 2) % 3;
+            if constexpr (FEAT) __syncwarp();       // the copy has read the buffer before the next transform overwrites it
         }
     }
 }
@@ -476,9 +501,10 @@ template <int L, int R2, int MODE>
 inline int solo_launch_t(const SoloTables &stb, const StParams &p, int sm_count, int64_t T, unsigned int *counter, cudaStream_t st)
 {
     const size_t smem = solo_smem_bytes<L, R2, MODE>(stb.pbl.words);
-    if (smem > 113u * 1024u) return B200AA_ERR_UNSUPPORTED;
+    constexpr int cap = MODE == kModeFeatures ? kSoloCtaCap : 113 * 1024;
+    if (smem > size_t(cap)) return B200AA_ERR_UNSUPPORTED;
     auto kern = st_solo_kernel<L, R2, MODE>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024) != cudaSuccess) return B200AA_ERR_CUDA;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cap) != cudaSuccess) return B200AA_ERR_CUDA;
     int occ = 1;
     constexpr int W = solo_warps<L, R2, MODE>();
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W, smem) != cudaSuccess) return B200AA_ERR_CUDA;

@@ -56,6 +56,28 @@ def one():
     res["kernel_ms"] = times[len(times) // 2]
     res["kernel_ms_min"] = times[0]
     res["frames_per_s"] = bench.CLIPS_PER_GPU * bench.FRAMES_PER_CLIP / (res["kernel_ms"] * 1e-3)
+    # ---- other shapes (kernel only): config 3's features (solo kernel) and other pair-kernel windows on the bench batch
+    def kernel_ms(c, fs, w, st_, reps=7):
+        nrm = pkg.clip_stats(c)
+        o = None
+        for _ in range(2):
+            o = pkg.feature_extraction_batch(c, fs, w, st_, norm=nrm, out=o)
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            pkg.feature_extraction_batch(c, fs, w, st_, norm=nrm, out=o)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        return ts[len(ts) // 2]
+    if os.environ.get("B200AA_AB_MORE"):
+        res["other_windows_ms"] = {"%d/%d" % (w, st_): kernel_ms(clips, 16000, w, st_) for w, st_ in ((1024, 512), (640, 320), (512, 256), (320, 160), (400, 160))}
+        c3 = torch.randint(-12000, 12000, (64, 2646000), generator=g, device="cuda", dtype=torch.int16)
+        res["config3_features_ms"] = kernel_ms(c3, 44100, 882, 441, reps=5)
+        res["config3_frames_per_s"] = 64 * 5999 / (res["config3_features_ms"] * 1e-3)
+        del c3
     # ---- end to end through the C ABI's host entry point (pinned host buffers, copies inside the timed region)
     import ctypes
     import time
@@ -86,11 +108,11 @@ def main(names):
                 continue
             env["B200AA_LIB"] = path
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one"], env=env, capture_output=True, text=True, timeout=120)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one"], env=env, capture_output=True, text=True, timeout=240)
             line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
             print(line[-1] if line else json.dumps({"lib": name, "error": (r.stderr or r.stdout)[-400:]}), flush=True)
         except subprocess.TimeoutExpired:
-            print(json.dumps({"lib": name, "error": "timeout (120 s)"}), flush=True)
+            print(json.dumps({"lib": name, "error": "timeout (240 s)"}), flush=True)
 
 
 if __name__ == "__main__":
