@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200aa.so")
 SOURCES = ["b200aa.cu"]
-DEPS = ["b200aa.cu", "common.cuh", "dft_codelets.cuh", "generic_kernel.cuh", "fast_kernel.cuh", "pair_kernel.cuh", "solo_kernel.cuh", "tables.inl",
+DEPS = ["b200aa.cu", "common.cuh", "dft_codelets.cuh", "generic_kernel.cuh", "fast_kernel.cuh", "pair_kernel.cuh", "solo_kernel.cuh", "sched.cuh", "tables.inl",
         os.path.join("..", "..", "include", "b200aa.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -154,8 +154,11 @@ struct b200aa_plan {
     int prefer = -1;                    // -1 = automatic, 0 / 1 / 2 / 3 = generic / register-tiled CTA / pair / solo kernel only (testing, A/B)
     // ring of work counters (one per in-flight launch of a persistent kernel).  A slot is handed out again only after
     // the launch that used it last has finished: that launch recorded the slot's event, the next user's stream waits on it.
-    static constexpr unsigned kSlots = 256;
-    unsigned int *d_counters = nullptr;
+    // A slot is kSlotBytes wide: the CTA / solo / generic kernels use its first word as their work counter, the pair kernel
+    // the whole slot as its per-warp range descriptors (csrc/sched.cuh: 8 bytes per resident warp).
+    static constexpr unsigned kSlots = 64;
+    static constexpr size_t kSlotBytes = 64 * 1024;
+    unsigned char *d_counters = nullptr;
     cudaEvent_t slot_event[kSlots] = {};
     bool slot_used[kSlots] = {};
     unsigned next_slot = 0;
@@ -322,7 +325,7 @@ extern "C" int b200aa_plan_create(b200aa_plan **out, int fs, int window, int ste
         rc = solo_plan_init(window, pblob, pbl, &pl->solo);
         if (rc != B200AA_OK) return cuda_fail(cudaGetLastError(), "solo_plan_init");
     }
-    CK(cudaMalloc(&pl->d_counters, b200aa_plan::kSlots * sizeof(unsigned int)));
+    CK(cudaMalloc(&pl->d_counters, b200aa_plan::kSlots * b200aa_plan::kSlotBytes));
     *out = pl.release();
     return B200AA_OK;
 }
@@ -336,7 +339,7 @@ static int slot_acquire(b200aa_plan *pl, cudaStream_t st, unsigned *slot, unsign
     if (!pl->slot_event[s]) CK(cudaEventCreateWithFlags(&pl->slot_event[s], cudaEventDisableTiming));
     if (pl->slot_used[s]) CK(cudaStreamWaitEvent(st, pl->slot_event[s], 0));
     *slot = s;
-    *ctr = pl->d_counters + s;
+    *ctr = reinterpret_cast<unsigned int *>(pl->d_counters + size_t(s) * b200aa_plan::kSlotBytes);
     return B200AA_OK;
 }
 static int slot_done(b200aa_plan *pl, cudaStream_t st, unsigned slot)
@@ -778,7 +781,7 @@ extern "C" int b200aa_st_features(const b200aa_plan *plan, const void *d_sig, in
         unsigned slot = 0;
         unsigned int *ctr = nullptr;
         if ((rc = slot_acquire(pl, st, &slot, &ctr)) != B200AA_OK) return rc;
-        rc = pair_launch_features(pl->pair, p, pl->sm_count, T, ctr, g_pair_dump, st);
+        rc = pair_launch_features(pl->pair, p, pl->sm_count, T, reinterpret_cast<unsigned long long *>(ctr), b200aa_plan::kSlotBytes, g_pair_dump, st);
         const int rc2 = slot_done(pl, st, slot);
         if (rc == B200AA_OK) { g_launches.fetch_add(1, std::memory_order_relaxed); return rc2; }
         if (rc != B200AA_ERR_UNSUPPORTED) return rc == B200AA_ERR_CUDA ? cuda_fail(cudaGetLastError(), "pair kernel") : rc;

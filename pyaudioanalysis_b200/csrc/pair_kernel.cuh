@@ -15,9 +15,9 @@
 //   * the spectral rows reuse the half-warp dense pass of fast_kernel.cuh (two frames per warp), the mel / chroma / DCT
 //     contractions are shared-memory dot products over the two |X| rows; feature rows collect in an [8 x 34] tile per warp
 //     and leave as 32-byte row segments.
-// Work items (clip, run of pairs) are handed out by one atomic per item, long runs first and short runs last, and every
-// run starts one pair early (flux and the deltas need frame t - 1), so results do not depend on how a clip was cut.
-// (Measured and rejected: an equal static share per warp + a dynamic tail -- 0.91-0.92 ms against 0.90 ms for this scheme.)
+// Work: every warp starts with an equal contiguous share of the launch's pair steps and takes it in chunks of a few pairs;
+// a warp that runs dry steals the back half of somebody's remainder (sched.cuh).  A run starts one pair early (flux and the
+// deltas need frame t - 1) and pairs are always (2q, 2q + 1), so results do not depend on how a clip was cut.
 #pragma once
 #include "common.cuh"
 #include "dft_codelets.cuh"
@@ -25,6 +25,7 @@
 #include <cstring>
 #include <utility>
 #include "fast_kernel.cuh"
+#include "sched.cuh"
 
 namespace b200aa {
 
@@ -120,10 +121,7 @@ struct PairParams {
     const int *pblob;          // tables above
     PairBlobLayout pbl;
     const float2 *tw;          // [R][32] inter-pass twiddles
-    unsigned int *counter;     // work counter (zeroed in-stream before the launch)
-    // pairs [0, P) of a clip are cut into n_big runs of seg_big pairs followed by runs of seg_small pairs;
-    // item = run * n_clips + clip, so every clip's long runs are handed out before anybody's short ones
-    int seg_big, n_big, seg_small, segs_per_clip;
+    StealParams sched;         // work distribution (sched.cuh): g = clip * sched.per_clip + pair
     float *dbg;                // optional dump of the |X| rows [clip][frame][K] (debugging)
 };
 
@@ -542,6 +540,20 @@ __device__ __forceinline__ void tile_store(const float *fv, int tile_n, int tile
     }
 }
 
+// the pending rows of a warp's tile leave; row 0 of the tile buffer becomes the last row written (the deltas' predecessor)
+__device__ __forceinline__ void tile_flush(float *fv, int &tile_n, int &tile_t0, float *out_clip, int64_t t_stride, int n_out, int lane)
+{
+    if (tile_n > 0) {
+        tile_store(fv, tile_n, tile_t0, out_clip, t_stride, n_out, lane);
+        __syncwarp();
+        fv[lane] = fv[tile_n * kFvStride + lane];
+        if (lane < 4) fv[32 + lane] = fv[tile_n * kFvStride + 32 + lane];     // incl. the row sum (slot 34)
+        tile_t0 += tile_n;
+        tile_n = 0;
+        __syncwarp();
+    }
+}
+
 // ----------------------------------------------------------------------------------------------
 // kernel
 // ----------------------------------------------------------------------------------------------
@@ -574,33 +586,54 @@ __global__ void __launch_bounds__(32 * pair_warps<R>(), kPairMinBlocks) st_pair_
     const int half = lane >> 4, l16 = lane & 15;
     const unsigned FULLM = 0xffffffffu;
 
+    const unsigned wglob = blockIdx.x * unsigned(pair_warps<R>()) + unsigned(warp);
+    if (lane == 0) sched_begin(pp.sched, wglob);
+    __syncwarp();
+    const int per_clip = int(pp.sched.per_clip);
+    // ---- the run in progress (all of it warp-uniform: the chunk bounds come out of sched_next as lane-0 broadcasts)
+    unsigned run_b = 0xffffffffu, run_q = 0xffffffffu;          // its clip and next pair; run_q = ~0: nothing carried
+    int tile_n = 0, tile_t0 = 0;
+    int zprev = 0;              // sign flips inside the first half of frame a (= second half of the previous b)
+    // pending feature rows -> global memory (tile_flush: always inlined -- an out-of-line call in the step loop costs the
+    // caller-saved registers)
+#define B200AA_PAIR_FLUSH(clip_index) tile_flush(wm.fv, tile_n, tile_t0, p.out + size_t(clip_index) * p.n_out * p.t_stride, p.t_stride, p.n_out, lane)
+
+    unsigned inc = pp.sched.chunk;      // pairs of the next claim (sched_claim adapts it)
     for (;;) {
-        unsigned item = 0;
-        if (lane == 0) item = atomicAdd(pp.counter, 1u);
-        item = __shfl_sync(FULLM, item, 0);
-        if (int64_t(item) >= p.n_items) break;
-        const int seg = int(item / unsigned(p.n_clips));
-        const int64_t b = item - unsigned(seg) * unsigned(p.n_clips);
+        unsigned g0 = 0, g1 = 0;
+        const int got = sched_next(pp.sched, blockIdx.x * unsigned(pair_warps<R>()) + unsigned(warp), lane, inc, g0, g1);
+        if (got == 0) break;
+        if (got == 2) continue;
+        while (g0 < g1) {                                          // a chunk may run over the end of a clip
+        const unsigned cb = g0 / unsigned(per_clip);
+        const int q0 = int(g0 - cb * unsigned(per_clip));
+        int qe = q0 + int(g1 - g0);
+        qe = qe < per_clip ? qe : per_clip;
+        const int64_t b = int64_t(cb);
+        const bool cont = cb == run_b && unsigned(q0) == run_q;     // the run goes on: state carried, no halo
+        if (!cont) B200AA_PAIR_FLUSH(run_b);                        // a new run: the previous one's tile leaves first
+        // the clip's values (a handful of cached loads per chunk; kept local so that nothing but the run state is carried)
         const int64_t len = p.len ? p.len[b] : p.n_samples;
         const int T = int(len < N ? 0 : (len - N) / step + 1);
         const int NP = (T + 1) >> 1;                               // pairs of this clip
-        int q0, q1;
-        if (seg < pp.n_big) { q0 = seg * pp.seg_big; q1 = q0 + pp.seg_big; }
-        else { q0 = pp.n_big * pp.seg_big + (seg - pp.n_big) * pp.seg_small; q1 = q0 + pp.seg_small; }
-        if (q0 >= NP) continue;
-        q1 = q1 < NP ? q1 : NP;
         const b200aa_clip_norm nm = p.norm[b];
         const bool is16 = p.dtype == B200AA_DTYPE_I16;
-        const char *clip = reinterpret_cast<const char *>(p.sig) + size_t(b) * p.clip_stride * (is16 ? 2 : 4);
+        const char *const clip = reinterpret_cast<const char *>(p.sig) + size_t(b) * p.clip_stride * (is16 ? 2 : 4);
         const float M0 = is16 ? 8421376.f : 0.f;                   // u = M0 + x exactly (2^23 + 2^15 trick for int16)
         const float cmv = M0 + nm.m;                                // u - cmv = x - m
         const bool two_sided = !(nm.hi > nm.lo);                    // a sample may equal the clip mean: count both masks
         const float inv_a2n = 1.f / (nm.a * nm.a * float(N));
         const float fscale = nm.a * (0.5f / float(K));
-
-        bool fresh = true;          // no state carried from a previous pair (first step of the item)
-        int tile_n = 0, tile_t0 = 2 * q0;
-        int zprev = 0;              // sign flips inside the first half of frame a (= second half of the previous b)
+        bool fresh = !cont;         // no state carried from a previous pair: the run starts one pair early
+        if (!cont) {
+            tile_t0 = 2 * q0;
+            zprev = 0;
+        }
+        g0 += unsigned(qe - q0);
+        run_b = cb;
+        run_q = 0xffffffffu;
+        if (q0 >= NP) continue;                                    // ragged batch: beyond this clip's last pair
+        const int q1 = qe < NP ? qe : NP;
         // samples: lane l holds samples 32 r + l of both frames of a pair, as exact floats M0 + x.
         // (Measured and rejected: issuing the loads of pair q + 1 in the middle of step q -- the 50 extra live registers
         // cost more in spills than the hidden latency gains, 0.94 vs 0.89 ms.)
@@ -618,7 +651,7 @@ __global__ void __launch_bounds__(32 * pair_warps<R>(), kPairMinBlocks) st_pair_
                 for (int r = 0; r < R; ++r) { wa[r] = __ldg(pa + 32 * r); wb[r] = __ldg(pb + 32 * r); }
             }
         };
-        for (int q = q0 - (q0 > 0 ? 1 : 0); q < q1; ++q) {
+        for (int q = q0 - ((fresh && q0 > 0) ? 1 : 0); q < q1; ++q) {
             const bool store = q >= q0;
             const int ta = 2 * q;
             const bool bvalid = ta + 1 < T;
@@ -822,23 +855,20 @@ __global__ void __launch_bounds__(32 * pair_warps<R>(), kPairMinBlocks) st_pair_
 #pragma unroll
             for (int j = 0; j < C; ++j) wm.rowp[lane + 32 * j] = rowbn[lane + 32 * j];
 
-            // ---- tile bookkeeping / store
+            // ---- tile bookkeeping: full tiles leave at once, a partial one when the run ends
             if (store) {
                 tile_n += bvalid ? 2 : 1;
-                if (tile_n == 8 || q == q1 - 1) {
-                    tile_store(wm.fv, tile_n, tile_t0, p.out + size_t(b) * p.n_out * p.t_stride, p.t_stride, p.n_out, lane);
-                    __syncwarp();
-                    wm.fv[lane] = wm.fv[tile_n * kFvStride + lane];
-                    if (lane < 4) wm.fv[32 + lane] = wm.fv[tile_n * kFvStride + 32 + lane];     // incl. the row sum (slot 34)
-                    tile_t0 += tile_n;
-                    tile_n = 0;
-                    __syncwarp();
-                }
+                if (tile_n == 8) B200AA_PAIR_FLUSH(cb);
             }
             fresh = false;
             __syncwarp();                    // the copy above has read the buffer before the next step's pass 1 overwrites it
         }
+        if (q1 < NP) run_q = unsigned(q1);
+        else B200AA_PAIR_FLUSH(cb);          // end of the clip (an odd frame count leaves a partial tile)
+        }
     }
+    B200AA_PAIR_FLUSH(run_b);
+#undef B200AA_PAIR_FLUSH
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -975,8 +1005,8 @@ inline int pair_plan_init(int window, const std::vector<int> &h_pblob, const Pai
 
 #ifndef B200AA_LAYOUT_ONLY
 template <int R, bool SHARED>
-inline int pair_launch_t(const PairTables &pt, const StParams &p, int sm_count, int64_t T, unsigned int *counter, float *dbg,
-                         cudaStream_t st)
+inline int pair_launch_t(const PairTables &pt, const StParams &p, int sm_count, int64_t T, unsigned long long *ranges, size_t ranges_cap,
+                         float *dbg, cudaStream_t st)
 {
     const size_t smem = pair_smem_bytes<R>(pt.pbl.words);
     if (smem > size_t(kPairCtaCap)) return B200AA_ERR_UNSUPPORTED;
@@ -991,64 +1021,59 @@ inline int pair_launch_t(const PairTables &pt, const StParams &p, int sm_count, 
     pp.tw = pt.d_tw;
     pp.pblob = pt.d_pblob;
     pp.pbl = pt.pbl;
-    pp.counter = counter;
     pp.dbg = dbg;
     const int64_t NP = (T + 1) / 2;                                  // pairs per (full-length) clip
     constexpr int kPairWarps = pair_warps<R>();
-    const int64_t slots = int64_t(sm_count) * occ * kPairWarps;      // resident warps
     const int64_t total = NP * p.n_clips;
-    int64_t share = (total + slots - 1) / slots;                     // pairs per warp if perfectly balanced
-    if (share < 1) share = 1;
-    // long runs (a third of a warp's share, cheap halo) for the first ~3/4 of every clip, short ones to level the tail
-    int64_t small = share / 10;
-    small = small < 4 ? 4 : (small > 48 ? 48 : small);
-    int64_t big = share / 3;
-    big = big < small ? small : big;
-    if (big > NP) big = NP;
-    if (small > NP) small = NP;
-    if (const char *ov = getenv("B200AA_PAIR_SEG")) {                // tuning override: "big,small"
+    if (total <= 0) return B200AA_OK;                                // no clip has a frame
+    if (total >= (int64_t(1) << 31)) return B200AA_ERR_UNSUPPORTED;
+    // every resident warp gets an equal contiguous share (sched.cuh); small launches use as many warps as they have pairs
+    int64_t grid = int64_t(sm_count) * occ;
+    if (grid * kPairWarps > total) grid = (total + kPairWarps - 1) / kPairWarps;
+    const int64_t n_warps = grid * kPairWarps;
+    if (size_t(n_warps) * sizeof(unsigned long long) > ranges_cap) return B200AA_ERR_UNSUPPORTED;
+    long chunk = 8, min_steal = 2;
+    if (const char *ov = getenv("B200AA_PAIR_STEAL")) {              // tuning override: "chunk,min_steal"
         long a = 0, b2 = 0;
-        if (sscanf(ov, "%ld,%ld", &a, &b2) == 2 && a > 0 && b2 > 0) { big = a < NP ? a : NP; small = b2 < NP ? b2 : NP; }
+        if (sscanf(ov, "%ld,%ld", &a, &b2) == 2 && a > 0 && b2 > 1) { chunk = a; min_steal = b2; }
     }
-    int64_t n_big = (NP * 3 / 4) / big;
-    if (total <= slots * 2) { n_big = 0; }                           // tiny launches: latency wins, short runs only
-    const int64_t left = NP - n_big * big;
-    const int64_t n_small = (left + small - 1) / small;
-    pp.seg_big = int(big); pp.n_big = int(n_big); pp.seg_small = int(small);
-    pp.segs_per_clip = int(n_big + n_small);
-    pp.st.n_items = int64_t(pp.segs_per_clip) * p.n_clips;
-    if (pp.st.n_items >= (int64_t(1) << 31) || T >= (int64_t(1) << 30)) return B200AA_ERR_UNSUPPORTED;
-    int64_t grid = (pp.st.n_items + kPairWarps - 1) / kPairWarps;
-    if (grid > int64_t(sm_count) * occ) grid = int64_t(sm_count) * occ;
+    pp.sched.ranges = ranges;
+    pp.sched.n_warps = unsigned(n_warps);
+    pp.sched.total = unsigned(total);
+    pp.sched.per_clip = unsigned(NP);
+    pp.sched.chunk = unsigned(chunk);
+    pp.sched.min_steal = unsigned(min_steal);
+    pp.st.n_items = total;
     if (getenv("B200AA_DEBUG"))
-        fprintf(stderr, "[b200aa] pair kernel R=%d shared=%d: smem %zu B, %d CTAs/SM, grid %lld, %lld items (%d x %d + %lld x %d pairs per clip)\n",
-                R, int(SHARED), smem, occ, (long long)grid, (long long)pp.st.n_items, pp.n_big, pp.seg_big, (long long)n_small, pp.seg_small);
-    if (cudaMemsetAsync(counter, 0, sizeof(unsigned int), st) != cudaSuccess) return B200AA_ERR_CUDA;
+        fprintf(stderr, "[b200aa] pair kernel R=%d shared=%d: smem %zu B, %d CTAs/SM x %d warps, grid %lld, %lld pairs (%lld per clip), chunk %ld, min steal %ld\n",
+                R, int(SHARED), smem, occ, kPairWarps, (long long)grid, (long long)total, (long long)NP, chunk, min_steal);
+    if (cudaMemsetAsync(ranges, 0, size_t(n_warps) * sizeof(unsigned long long), st) != cudaSuccess) return B200AA_ERR_CUDA;
     kern<<<(unsigned)grid, 32 * kPairWarps, smem, st>>>(pp);
     return cudaPeekAtLastError() == cudaSuccess ? B200AA_OK : B200AA_ERR_CUDA;
 }
 
 template <int R>
-inline int pair_launch_r(const PairTables &pt, const StParams &p, int sm_count, int64_t T, unsigned int *counter, float *dbg, cudaStream_t st)
+inline int pair_launch_r(const PairTables &pt, const StParams &p, int sm_count, int64_t T, unsigned long long *ranges, size_t ranges_cap,
+                         float *dbg, cudaStream_t st)
 {
     constexpr int N = 32 * R;
-    if (PairShape<R>::kShareable && p.step == N / 2) return pair_launch_t<R, PairShape<R>::kShareable>(pt, p, sm_count, T, counter, dbg, st);
-    return pair_launch_t<R, false>(pt, p, sm_count, T, counter, dbg, st);
+    if (PairShape<R>::kShareable && p.step == N / 2) return pair_launch_t<R, PairShape<R>::kShareable>(pt, p, sm_count, T, ranges, ranges_cap, dbg, st);
+    return pair_launch_t<R, false>(pt, p, sm_count, T, ranges, ranges_cap, dbg, st);
 }
 
 // feature launch through the pair kernel; B200AA_ERR_UNSUPPORTED = let another kernel take it
-inline int pair_launch_features(const PairTables &pt, const StParams &p, int sm_count, int64_t T, unsigned int *counter, float *dbg,
-                                cudaStream_t st)
+inline int pair_launch_features(const PairTables &pt, const StParams &p, int sm_count, int64_t T, unsigned long long *ranges, size_t ranges_cap,
+                                float *dbg, cudaStream_t st)
 {
     // 2-byte (int16) / 4-byte (float) loads need nothing beyond natural alignment; frames must fit 32-bit indices
     switch (pt.R) {
-    case 10: return pair_launch_r<10>(pt, p, sm_count, T, counter, dbg, st);
-    case 15: return pair_launch_r<15>(pt, p, sm_count, T, counter, dbg, st);
-    case 16: return pair_launch_r<16>(pt, p, sm_count, T, counter, dbg, st);
-    case 32: return pair_launch_r<32>(pt, p, sm_count, T, counter, dbg, st);
-    case 20: return pair_launch_r<20>(pt, p, sm_count, T, counter, dbg, st);
-    case 25: return pair_launch_r<25>(pt, p, sm_count, T, counter, dbg, st);
-    case 30: return pair_launch_r<30>(pt, p, sm_count, T, counter, dbg, st);
+    case 10: return pair_launch_r<10>(pt, p, sm_count, T, ranges, ranges_cap, dbg, st);
+    case 15: return pair_launch_r<15>(pt, p, sm_count, T, ranges, ranges_cap, dbg, st);
+    case 16: return pair_launch_r<16>(pt, p, sm_count, T, ranges, ranges_cap, dbg, st);
+    case 32: return pair_launch_r<32>(pt, p, sm_count, T, ranges, ranges_cap, dbg, st);
+    case 20: return pair_launch_r<20>(pt, p, sm_count, T, ranges, ranges_cap, dbg, st);
+    case 25: return pair_launch_r<25>(pt, p, sm_count, T, ranges, ranges_cap, dbg, st);
+    case 30: return pair_launch_r<30>(pt, p, sm_count, T, ranges, ranges_cap, dbg, st);
     default: return B200AA_ERR_UNSUPPORTED;
     }
 }
