@@ -140,6 +140,14 @@ int b200aa_mid_pool(const float *d_st, int64_t n_clips, int n_feats, int64_t n_f
 int b200aa_long_term_mean(const float *d_mid, int64_t n_clips, int n_rows, int64_t n_windows,
                           float *d_out, void *stream);
 
+/* Feature vectors for the classifiers that consume the mid-term matrix: d_out float32
+ * [n_clips, n_windows, n_rows], vector j of clip b = (d_mid[b, :, j] - mean) / std -- the transpose the per-window loops
+ * build one column at a time.  d_mean / d_std: float32 [n_rows] on the device.
+ * Replaces: `feature_vector = (mt_feats[:, col_index] - mean) / std` per window (audioSegmentation.py:581-584,
+ * audioTrainTest.py:1091) and per short-term frame (audioSegmentation.py:744-748, with d_mid = the [68 x T] matrix). */
+int b200aa_normalize_windows(const float *d_mid, int64_t n_clips, int n_rows, int64_t n_windows,
+                             const float *d_mean, const float *d_std, float *d_out, void *stream);
+
 /* ------------------------------------------------------------------ host entry points --
  * Same operations on HOST buffers: pinned or pageable input is copied to the device, the
  * kernels run, the result is copied back and the call returns after the stream drained.

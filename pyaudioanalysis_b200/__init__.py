@@ -8,10 +8,10 @@ values and error behaviour) on top of hand-written sm_100a CUDA (``libb200aa.so`
 ``include/b200aa.h``).  ``install()`` rebinds those attributes on an imported pyAudioAnalysis.
 There is no CPU fallback.
 """
-from . import ShortTermFeatures, MidTermFeatures  # noqa: F401
+from . import ShortTermFeatures, MidTermFeatures, consumers  # noqa: F401
 from .batch import (feature_extraction_batch, mid_feature_extraction_batch, clip_stats,  # noqa: F401
                     spectrogram_batch, chromagram_batch)
 from .install import install, uninstall  # noqa: F401
 
-__all__ = ["ShortTermFeatures", "MidTermFeatures", "feature_extraction_batch", "mid_feature_extraction_batch",
+__all__ = ["ShortTermFeatures", "MidTermFeatures", "consumers", "feature_extraction_batch", "mid_feature_extraction_batch",
            "spectrogram_batch", "chromagram_batch", "clip_stats", "install", "uninstall"]

@@ -678,6 +678,42 @@ extern "C" int b200aa_long_term_mean(const float *d_mid, int64_t n_clips, int n_
     return B200AA_OK;
 }
 
+// (mid[b, f, j] - mean[f]) / std[f] -> out[b, j, f]: 32 x 32 tiles through shared memory, both sides coalesced
+// (audioSegmentation.py:581-584: one column of the mid-term matrix at a time)
+__global__ void normalize_windows_kernel(const float *__restrict__ mid, int n_rows, int64_t n_windows, const float *__restrict__ mean,
+                                         const float *__restrict__ sd, float *__restrict__ out)
+{
+    __shared__ float tile[32][33];
+    const int64_t b = blockIdx.z;
+    const int64_t j0 = int64_t(blockIdx.x) * 32;
+    const int f0 = blockIdx.y * 32;
+    const float *src = mid + b * n_rows * n_windows;
+    float *dst = out + b * n_rows * n_windows;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int f = f0 + r;
+        const int64_t j = j0 + threadIdx.x;
+        if (f < n_rows && j < n_windows) tile[r][threadIdx.x] = (src[int64_t(f) * n_windows + j] - mean[f]) / sd[f];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int64_t j = j0 + r;
+        const int f = f0 + threadIdx.x;
+        if (f < n_rows && j < n_windows) dst[j * n_rows + f] = tile[threadIdx.x][r];
+    }
+}
+
+extern "C" int b200aa_normalize_windows(const float *d_mid, int64_t n_clips, int n_rows, int64_t n_windows, const float *d_mean,
+                                        const float *d_std, float *d_out, void *stream)
+{
+    if (!d_mid || !d_out || !d_mean || !d_std || n_clips < 0 || n_rows < 1 || n_windows < 0) return B200AA_ERR_INVALID;
+    if (n_clips == 0 || n_windows == 0) return B200AA_OK;
+    if (n_clips > 65535 || (n_rows + 31) / 32 > 65535) return B200AA_ERR_UNSUPPORTED;
+    const dim3 grid((unsigned)((n_windows + 31) / 32), (unsigned)((n_rows + 31) / 32), (unsigned)n_clips), block(32, 8);
+    normalize_windows_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(d_mid, n_rows, n_windows, d_mean, d_std, d_out);
+    CK_LAUNCH("normalize_windows_kernel");
+    return B200AA_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernel 1 launchers
 // ------------------------------------------------------------------------------------------------
