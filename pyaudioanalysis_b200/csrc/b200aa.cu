@@ -826,7 +826,7 @@ extern "C" int b200aa_st_features(const b200aa_plan *plan, const void *d_sig, in
         unsigned slot = 0;
         unsigned int *ctr = nullptr;
         if ((rc = slot_acquire(pl, st, &slot, &ctr)) != B200AA_OK) return rc;
-        rc = solo_launch_mode<kModeFeatures>(pl->solo, p, pl->sm_count, T, ctr, st);
+        rc = solo_launch_mode<kModeFeatures>(pl->solo, p, pl->sm_count, T, ctr, b200aa_plan::kSlotBytes, st);
         const int rc2 = slot_done(pl, st, slot);
         if (rc == B200AA_OK) { g_launches.fetch_add(1, std::memory_order_relaxed); return rc2; }
         if (rc != B200AA_ERR_UNSUPPORTED) return rc == B200AA_ERR_CUDA ? cuda_fail(cudaGetLastError(), "solo kernel") : rc;
@@ -870,7 +870,7 @@ extern "C" int b200aa_spectrogram(const b200aa_plan *plan, const void *d_sig, in
         unsigned slot = 0;
         unsigned int *ctr = nullptr;
         if ((rc = slot_acquire(pl, st_, &slot, &ctr)) != B200AA_OK) return rc;
-        rc = solo_launch_mode<kModeSpectrogram>(pl->solo, p, pl->sm_count, p.rows_launch, ctr, st_);
+        rc = solo_launch_mode<kModeSpectrogram>(pl->solo, p, pl->sm_count, p.rows_launch, ctr, b200aa_plan::kSlotBytes, st_);
         const int rc2 = slot_done(pl, st_, slot);
         if (rc == B200AA_OK) { g_launches.fetch_add(1, std::memory_order_relaxed); return rc2; }
         if (rc != B200AA_ERR_UNSUPPORTED) return rc == B200AA_ERR_CUDA ? cuda_fail(cudaGetLastError(), "solo kernel") : rc;
@@ -920,7 +920,7 @@ extern "C" int b200aa_chromagram(const b200aa_plan *plan, const void *d_sig, int
         unsigned slot = 0;
         unsigned int *ctr = nullptr;
         if ((rc = slot_acquire(pl, st, &slot, &ctr)) != B200AA_OK) return rc;
-        rc = solo_launch_mode<kModeChromagram>(pl->solo, p, pl->sm_count, p.rows_launch, ctr, st);
+        rc = solo_launch_mode<kModeChromagram>(pl->solo, p, pl->sm_count, p.rows_launch, ctr, b200aa_plan::kSlotBytes, st);
         if (slot_done(pl, st, slot) != B200AA_OK) return B200AA_ERR_CUDA;
         if (rc == B200AA_OK) g_launches.fetch_add(1, std::memory_order_relaxed);
         else if (rc != B200AA_ERR_UNSUPPORTED) return rc == B200AA_ERR_CUDA ? cuda_fail(cudaGetLastError(), "solo kernel") : rc;

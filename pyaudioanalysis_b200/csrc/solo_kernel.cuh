@@ -99,8 +99,9 @@ struct SoloParams {
     const float2 *tw, *twp;
     const int *pblob;
     PairBlobLayout pbl;
-    unsigned int *counter;
-    int seg_big, n_big, seg_small, segs_per_clip;       // runs of pairs per clip (as in the pair kernel)
+    unsigned int *counter;                              // row modes: work counter over the run list below
+    int seg_big, n_big, seg_small, segs_per_clip;       // row modes: runs of pairs per clip, long ones first (rows need no halo)
+    StealParams sched;                                  // features: static shares + steal-half (sched.cuh), as in the pair kernel
 };
 
 template <int L, int R2, int MODE = kModeFeatures>
@@ -179,24 +180,59 @@ __global__ void __launch_bounds__(32 * solo_warps<L, R2, MODE>(), solo_min_block
     const int half = lane >> 4, l16 = lane & 15;
     const unsigned FULLM = 0xffffffffu;
 
+    // ---- features: the run in progress (warp-uniform; see pair_kernel.cuh)
+    unsigned g0 = 0, g1 = 0, inc = FEAT ? pp.sched.chunk : 0u;
+    unsigned run_b = 0xffffffffu, run_q = 0xffffffffu;
+    int tile_n = 0, tile_t0 = 0;
+    if constexpr (FEAT) {
+        if (lane == 0) sched_begin(pp.sched, blockIdx.x * unsigned(solo_warps<L, R2, MODE>()) + unsigned(warp));
+        __syncwarp();
+    }
+#define B200AA_SOLO_FLUSH(clip_index) tile_flush(wm.fv, tile_n, tile_t0, p.out + size_t(clip_index) * p.n_out * p.t_stride, p.t_stride, p.n_out, lane)
+
     for (;;) {
-        unsigned item = 0;
-        if (lane == 0) item = atomicAdd(pp.counter, 1u);
-        item = __shfl_sync(FULLM, item, 0);
-        if (int64_t(item) >= p.n_items) break;
-        const int seg = int(item / unsigned(p.n_clips));
-        const int64_t b = item - unsigned(seg) * unsigned(p.n_clips);
-        const int64_t len = p.len ? p.len[b] : p.n_samples;
-        // features: frames of the clip; spectrogram / chromagram: the rows of this launch (rows >= rows_valid are zero)
-        const int T = int(MODE == kModeFeatures ? (len < N ? 0 : (len - N) / step + 1) : p.rows_launch);
+        int64_t b;
+        int q0, q1, T, NP;
+        bool fresh = true;
+        if constexpr (FEAT) {
+            if (g0 >= g1) {
+                const int got = sched_next(pp.sched, blockIdx.x * unsigned(solo_warps<L, R2, MODE>()) + unsigned(warp), lane, inc, g0, g1);
+                if (got == 0) break;
+                if (got == 2) continue;
+            }
+            const unsigned per_clip = pp.sched.per_clip;
+            const unsigned cb = g0 / per_clip;
+            q0 = int(g0 - cb * per_clip);
+            int qe = q0 + int(g1 - g0);
+            qe = qe < int(per_clip) ? qe : int(per_clip);
+            g0 += unsigned(qe - q0);                                // a chunk may run over the end of a clip
+            b = int64_t(cb);
+            const bool cont = cb == run_b && unsigned(q0) == run_q; // the run goes on: state carried, no halo
+            if (!cont) { B200AA_SOLO_FLUSH(run_b); tile_t0 = 2 * q0; }
+            fresh = !cont;
+            run_b = cb;
+            run_q = 0xffffffffu;
+            const int64_t len = p.len ? p.len[b] : p.n_samples;
+            T = int(len < N ? 0 : (len - N) / step + 1);
+            NP = (T + 1) >> 1;
+            if (q0 >= NP) continue;                                 // ragged batch: beyond this clip's last pair
+            q1 = qe < NP ? qe : NP;
+        } else {
+            unsigned item = 0;
+            if (lane == 0) item = atomicAdd(pp.counter, 1u);
+            item = __shfl_sync(FULLM, item, 0);
+            if (int64_t(item) >= p.n_items) break;
+            const int seg = int(item / unsigned(p.n_clips));
+            b = item - unsigned(seg) * unsigned(p.n_clips);
+            T = int(p.rows_launch);                                 // the rows of this launch (rows >= rows_valid are zero)
+            NP = (T + 1) >> 1;
+            if (seg < pp.n_big) { q0 = seg * pp.seg_big; q1 = q0 + pp.seg_big; }
+            else { q0 = pp.n_big * pp.seg_big + (seg - pp.n_big) * pp.seg_small; q1 = q0 + pp.seg_small; }
+            if (q0 >= NP) continue;
+            q1 = q1 < NP ? q1 : NP;
+        }
         const int n_valid = MODE == kModeFeatures ? T : int(p.rows_valid);
         const int64_t origin = MODE == kModeFeatures ? 0 : p.origin;
-        const int NP = (T + 1) >> 1;
-        int q0, q1;
-        if (seg < pp.n_big) { q0 = seg * pp.seg_big; q1 = q0 + pp.seg_big; }
-        else { q0 = pp.n_big * pp.seg_big + (seg - pp.n_big) * pp.seg_small; q1 = q0 + pp.seg_small; }
-        if (q0 >= NP) continue;
-        q1 = q1 < NP ? q1 : NP;
         const b200aa_clip_norm nm = p.norm[b];
         const bool is16 = p.dtype == B200AA_DTYPE_I16;
         const char *clip = reinterpret_cast<const char *>(p.sig) + size_t(b) * p.clip_stride * (is16 ? 2 : 4);
@@ -210,9 +246,7 @@ __global__ void __launch_bounds__(32 * solo_warps<L, R2, MODE>(), solo_min_block
         auto s16 = [&](int64_t n) -> float { return __int_as_float(0x4B000000 | (int(__ldg(c16 + n)) ^ 0x8000)); };
         auto s32 = [&](int64_t n) -> float { return __ldg(c32 + n); };
 
-        bool fresh = true;
-        int tile_n = 0, tile_t0 = 2 * q0;
-        const int halo = (MODE == kModeFeatures && q0 > 0) ? 1 : 0;
+        const int halo = (MODE == kModeFeatures && fresh && q0 > 0) ? 1 : 0;
         for (int q = q0 - halo; q < q1; ++q) {
             const bool store = q >= q0;
             const int ta = 2 * q;
@@ -423,21 +457,19 @@ __global__ void __launch_bounds__(32 * solo_warps<L, R2, MODE>(), solo_min_block
                 for (int j = 0; j < Kp / 32; ++j) wm.rowp[lane + 32 * j] = rowb[lane + 32 * j];
                 if (store) {
                     tile_n += bvalid ? 2 : 1;
-                    if (tile_n == 8 || q == q1 - 1) {
-                        tile_store(wm.fv, tile_n, tile_t0, p.out + size_t(b) * p.n_out * p.t_stride, p.t_stride, p.n_out, lane);
-                        __syncwarp();
-                        wm.fv[lane] = wm.fv[tile_n * kFvStride + lane];
-                        if (lane < 4) wm.fv[32 + lane] = wm.fv[tile_n * kFvStride + 32 + lane];
-                        tile_t0 += tile_n;
-                        tile_n = 0;
-                        __syncwarp();
-                    }
+                    if (tile_n == 8) B200AA_SOLO_FLUSH(b);          // full tiles leave at once, a partial one when the run ends
                 }
             }
             fresh = false;
             if constexpr (FEAT) __syncwarp();       // the copy has read the buffer before the next transform overwrites it
         }
+        if constexpr (FEAT) {
+            if (q1 < NP) run_q = unsigned(q1);
+            else B200AA_SOLO_FLUSH(b);              // end of the clip (an odd frame count leaves a partial tile)
+        }
     }
+    if constexpr (FEAT) B200AA_SOLO_FLUSH(run_b);
+#undef B200AA_SOLO_FLUSH
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -498,7 +530,8 @@ inline int solo_plan_init(int window, const std::vector<int> &h_pblob, const Pai
 
 #ifndef B200AA_LAYOUT_ONLY
 template <int L, int R2, int MODE>
-inline int solo_launch_t(const SoloTables &stb, const StParams &p, int sm_count, int64_t T, unsigned int *counter, cudaStream_t st)
+inline int solo_launch_t(const SoloTables &stb, const StParams &p, int sm_count, int64_t T, unsigned int *counter, size_t counter_cap,
+                         cudaStream_t st)
 {
     const size_t smem = solo_smem_bytes<L, R2, MODE>(stb.pbl.words);
     constexpr int cap = MODE == kModeFeatures ? kSoloCtaCap : 113 * 1024;
@@ -517,6 +550,35 @@ inline int solo_launch_t(const SoloTables &stb, const StParams &p, int sm_count,
     const int64_t NP = (T + 1) / 2;
     const int64_t slots = int64_t(sm_count) * occ * W;
     const int64_t total = NP * p.n_clips;
+    int64_t grid = int64_t(sm_count) * occ;
+    if (MODE == kModeFeatures) {
+        // static shares + steal-half (sched.cuh): the slot is the per-warp range table
+        if (total <= 0) return B200AA_OK;
+        if (total >= (int64_t(1) << 31)) return B200AA_ERR_UNSUPPORTED;
+        if (grid * W > total) grid = (total + W - 1) / W;
+        const int64_t n_warps = grid * W;
+        if (size_t(n_warps) * sizeof(unsigned long long) > counter_cap) return B200AA_ERR_UNSUPPORTED;
+        long chunk = 8, min_steal = 2;
+        if (const char *ov = getenv("B200AA_PAIR_STEAL")) {
+            long a = 0, b2 = 0;
+            if (sscanf(ov, "%ld,%ld", &a, &b2) == 2 && a > 0 && b2 > 1) { chunk = a; min_steal = b2; }
+        }
+        pp.sched.ranges = reinterpret_cast<unsigned long long *>(counter);
+        pp.sched.n_warps = unsigned(n_warps);
+        pp.sched.total = unsigned(total);
+        pp.sched.per_clip = unsigned(NP);
+        pp.sched.chunk = unsigned(chunk);
+        pp.sched.min_steal = unsigned(min_steal);
+        pp.seg_big = pp.n_big = pp.seg_small = pp.segs_per_clip = 0;
+        pp.st.n_items = total;
+        if (getenv("B200AA_DEBUG"))
+            fprintf(stderr, "[b200aa] solo kernel %dx%d features: smem %zu B, %d CTAs/SM x %d warps, grid %lld, %lld pairs\n", L, R2, smem, occ, W,
+                    (long long)grid, (long long)total);
+        if (cudaMemsetAsync(counter, 0, size_t(n_warps) * sizeof(unsigned long long), st) != cudaSuccess) return B200AA_ERR_CUDA;
+        kern<<<(unsigned)grid, 32 * W, smem, st>>>(pp);
+        return cudaPeekAtLastError() == cudaSuccess ? B200AA_OK : B200AA_ERR_CUDA;
+    }
+    pp.sched = StealParams{};
     int64_t share = (total + slots - 1) / slots;
     if (share < 1) share = 1;
     int64_t small = share / 10;
@@ -533,7 +595,7 @@ inline int solo_launch_t(const SoloTables &stb, const StParams &p, int sm_count,
     pp.segs_per_clip = int(n_big + n_small);
     pp.st.n_items = int64_t(pp.segs_per_clip) * p.n_clips;
     if (pp.st.n_items >= (int64_t(1) << 31) || T >= (int64_t(1) << 30)) return B200AA_ERR_UNSUPPORTED;
-    int64_t grid = (pp.st.n_items + W - 1) / W;
+    grid = (pp.st.n_items + W - 1) / W;
     if (grid > int64_t(sm_count) * occ) grid = int64_t(sm_count) * occ;
     if (grid < 1) grid = 1;
     if (getenv("B200AA_DEBUG"))
@@ -545,11 +607,12 @@ inline int solo_launch_t(const SoloTables &stb, const StParams &p, int sm_count,
 }
 
 template <int MODE>
-inline int solo_launch_mode(const SoloTables &stb, const StParams &p, int sm_count, int64_t T, unsigned int *counter, cudaStream_t st)
+inline int solo_launch_mode(const SoloTables &stb, const StParams &p, int sm_count, int64_t T, unsigned int *counter, size_t counter_cap,
+                            cudaStream_t st)
 {
-    if (stb.L == 21 && stb.R2 == 21) return solo_launch_t<21, 21, MODE>(stb, p, sm_count, T, counter, st);
-    if (stb.L == 20 && stb.R2 == 10) return solo_launch_t<20, 10, MODE>(stb, p, sm_count, T, counter, st);
-    if (stb.L == 20 && stb.R2 == 15) return solo_launch_t<20, 15, MODE>(stb, p, sm_count, T, counter, st);
+    if (stb.L == 21 && stb.R2 == 21) return solo_launch_t<21, 21, MODE>(stb, p, sm_count, T, counter, counter_cap, st);
+    if (stb.L == 20 && stb.R2 == 10) return solo_launch_t<20, 10, MODE>(stb, p, sm_count, T, counter, counter_cap, st);
+    if (stb.L == 20 && stb.R2 == 15) return solo_launch_t<20, 15, MODE>(stb, p, sm_count, T, counter, counter_cap, st);
     return B200AA_ERR_UNSUPPORTED;
 }
 #endif  // B200AA_LAYOUT_ONLY
