@@ -43,6 +43,15 @@ pkg.mid_feature_extraction_batch(clips, 16000, 8000, 4000, 800, 400)
 x = clips[0].cpu().numpy()
 pkg.ShortTermFeatures.chromagram(x[:16300], 16000, 800, 400)                      # clipped last frame (generic launch)
 from pyaudioanalysis_b200.hostpipe import HostPipeline
+# steal-half scheduler with more pair steps than warps and stealing forced by tiny claims (B200AA_PAIR_STEAL=1,2 in the
+# environment makes every warp's range change hands): 40 clips x 10 s
+if os.environ.get("B200AA_SANITIZE_STEAL"):
+    big = torch.from_numpy(np.stack([O.synth_clip(40 + i, 160000, 16000) for i in range(40)])).cuda()
+    lens_b = torch.randint(800, 160001, (40,), dtype=torch.int64, device="cuda")
+    pkg.feature_extraction_batch(big, 16000, 800, 400, lengths=lens_b)
+    pkg.feature_extraction_batch(big[:, :132300].contiguous(), 44100, 882, 441)
+from pyaudioanalysis_b200.consumers import normalize_windows_batch
+normalize_windows_batch(torch.randn(2, 136, 9, device="cuda"), np.zeros(136), np.ones(136))      # consumers: normalise + transpose
 hp = HostPipeline(16000, 800, 400, 24000, max_clips=6, device=0, bind_numa=False)
 hp.h_in[:] = clips.cpu().numpy()
 hp.run()

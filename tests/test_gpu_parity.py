@@ -214,6 +214,31 @@ def test_batch_and_ragged(P):
         check_features(outf[i].cpu().numpy(), O.feature_extraction(clips[i], 16000, 800, 400, deltas=False)[0], 400, f"f32 clip {i}")
 
 
+def test_work_stealing_is_invisible(P, monkeypatch):
+    """More pair steps than resident warps, ragged lengths, and the steal-half scheduler (csrc/sched.cuh) forced to hand
+    ranges over all the time (claims of one pair, any remainder stolen): outputs are bit-identical to the default
+    settings' and to a clip processed alone -- results do not depend on which warp computed which pairs -- for the pair
+    kernel (800 / 400) and the solo kernel (882 / 441)."""
+    import torch
+    rng = np.random.default_rng(77)
+    base = np.stack([O.synth_clip(200 + i, 48000, 16000) for i in range(8)])
+    clips = torch.from_numpy(np.concatenate([np.roll(base, 37 * k, axis=1) for k in range(40)])).cuda()       # 320 clips x 3 s
+    lens = torch.from_numpy(rng.integers(700, 48001, size=clips.shape[0]).astype(np.int64)).cuda()
+    lens[:8] = 48000
+    for fs, w, s in ((16000, 800, 400), (44100, 882, 441)):
+        monkeypatch.delenv("B200AA_PAIR_STEAL", raising=False)
+        ref = P.feature_extraction_batch(clips, fs, w, s, lengths=lens).clone()
+        for setting in ("1,2", "3,7", "64,2"):
+            monkeypatch.setenv("B200AA_PAIR_STEAL", setting)
+            got = P.feature_extraction_batch(clips, fs, w, s, lengths=lens)
+            assert torch.equal(got, ref), "results depend on the work distribution (%s, window %d)" % (setting, w)
+        monkeypatch.delenv("B200AA_PAIR_STEAL", raising=False)
+        alone = P.feature_extraction_batch(clips[5:6], fs, w, s)
+        assert torch.equal(alone[0], ref[5])
+        for i in (0, 3):
+            check_features(ref[i].cpu().numpy(), O.feature_extraction(base[i], fs, w, s)[0], w // 2, "stolen clip %d window %d" % (i, w))
+
+
 def test_directory_feature_extraction(P, tmp_path):
     """long-term averaged mid-term vectors per file of a folder, against the reference's own output
     on its 3_class test clips (8 kHz, 1 s, 12 per class; the silence class exercises near-digital-silence audio)."""
