@@ -851,9 +851,13 @@ __global__ void __launch_bounds__(32 * pair_warps<R>(), kPairMinBlocks) st_pair_
             // ---- spectral rows, mel / chroma / DCT: half-warp per frame over the two |X| rows
             rows_to_features<K>(rowa, rowbn, fresh ? rowa : wm.rowp, fresh, wm.fv[(ra - 1) * kFvStride + 34], cm_.dlane,
                                 rowa + S::PT0, msraw, mslog, mfold, rowa + S::CH0, fva, fvb, ftab, lane);
-            // frame b's row outlives the next transform beside the buffer (rows_to_features ends with a __syncwarp)
+            // frame b's row outlives the next transform beside the buffer (rows_to_features ends with a __syncwarp);
+            // 16 bytes per lane and instruction: both rows are 16-byte aligned and Kp is a multiple of 32
 #pragma unroll
-            for (int j = 0; j < C; ++j) wm.rowp[lane + 32 * j] = rowbn[lane + 32 * j];
+            for (int j = 0; j < (Kp / 4 + 31) / 32; ++j) {
+                const int i4 = lane + 32 * j;
+                if (i4 < Kp / 4) reinterpret_cast<float4 *>(wm.rowp)[i4] = reinterpret_cast<const float4 *>(rowbn)[i4];
+            }
 
             // ---- tile bookkeeping: full tiles leave at once, a partial one when the run ends
             if (store) {

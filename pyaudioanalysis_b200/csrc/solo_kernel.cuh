@@ -454,7 +454,10 @@ __global__ void __launch_bounds__(32 * solo_warps<L, R2, MODE>(), solo_min_block
                                     rowb + S::PT0, msraw, mslog, mfold, rowb + S::CH0, wm.fv + ra * kFvStride, wm.fv + rb * kFvStride, ftab, lane);
                 // frame b's row outlives the next transforms beside the buffer (rows_to_features ends with a __syncwarp)
 #pragma unroll
-                for (int j = 0; j < Kp / 32; ++j) wm.rowp[lane + 32 * j] = rowb[lane + 32 * j];
+                for (int j = 0; j < (Kp / 4 + 31) / 32; ++j) {      // 16 bytes per lane and instruction
+                    const int i4 = lane + 32 * j;
+                    if (i4 < Kp / 4) reinterpret_cast<float4 *>(wm.rowp)[i4] = reinterpret_cast<const float4 *>(rowb)[i4];
+                }
                 if (store) {
                     tile_n += bvalid ? 2 : 1;
                     if (tile_n == 8) B200AA_SOLO_FLUSH(b);          // full tiles leave at once, a partial one when the run ends

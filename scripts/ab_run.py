@@ -1,7 +1,7 @@
 """A/B several builds of libb200aa.so in ONE gpurun call: quick parity against the oracle + kernel timing per build.
 
-    python scripts/build_variants.py pw6 mb4                       # here (no GPU needed)
-    gpurun --timeout 300 -- 'python scripts/ab_run.py default pw6 mb4 | tee gpurun_out/ab.jsonl'
+    python scripts/build_variants.py p2x8 mb4                      # here (no GPU needed)
+    gpurun --timeout 300 -- 'python scripts/ab_run.py default p2x8 mb4 | tee gpurun_out/ab.jsonl'
 
 Every build runs in its own process (the library is chosen at import time through B200AA_LIB).  Prints one JSON line
 per build: {"lib", "parity_ok", "worst", "kernel_ms" (median of 20 launches, CUDA events around the fused kernel only),

@@ -1,8 +1,8 @@
 """Compile-time variants of libb200aa.so for A/B runs on the GPU box (the default library is untouched):
 
-    python scripts/build_variants.py pw6        # one
+    python scripts/build_variants.py p2x8       # one
     python scripts/build_variants.py            # all
-    gpurun -- 'python scripts/ab_run.py default pw6 | tee gpurun_out/ab.jsonl'
+    gpurun -- 'python scripts/ab_run.py default p2x8 | tee gpurun_out/ab.jsonl'
 
 Variants land in pyaudioanalysis_b200/variants/libb200aa_<name>.so and are selected per process with B200AA_LIB.
 """
@@ -15,8 +15,12 @@ sys.path.insert(0, ROOT)
 from pyaudioanalysis_b200 import build as B   # noqa: E402
 
 VARIANTS = {
-    # pair kernel with six warps per CTA: 12 warps per SM at up to 168 registers instead of 16 at 128
-    "pw6": ["-DB200AA_PAIR_MAXWARPS=6"],
+    # pair kernel: CTAs per SM x warps per CTA (default 1 x 24, the 800-sample window gets 20 by its shared memory)
+    "p2x8": ["-DB200AA_PAIR_MINBLOCKS=2", "-DB200AA_PAIR_MAXWARPS=8"],
+    "p1x20": ["-DB200AA_PAIR_MAXWARPS=20"],
+    # solo kernel, feature layout (default 1 x 24)
+    "s2x8": ["-DB200AA_SOLO_MINBLOCKS=2", "-DB200AA_SOLO_MAXWARPS=8"],
+    "s1x20": ["-DB200AA_SOLO_MAXWARPS=20"],
     # CTA kernel at 64 registers / 4 CTAs per SM
     "mb4": ["-DB200AA_FAST_MINBLOCKS=4"],
     # reference points for bisecting: scalar butterflies / IEEE MUFU wrappers
