@@ -1039,7 +1039,7 @@ inline int pair_launch_t(const PairTables &pt, const StParams &p, int sm_count, 
     long chunk = 8, min_steal = 2;
     if (const char *ov = getenv("B200AA_PAIR_STEAL")) {              // tuning override: "chunk,min_steal"
         long a = 0, b2 = 0;
-        if (sscanf(ov, "%ld,%ld", &a, &b2) == 2 && a > 0 && b2 > 1) { chunk = a; min_steal = b2; }
+        if (sscanf(ov, "%ld,%ld", &a, &b2) == 2 && a > 0 && a <= 65536 && b2 > 1 && b2 <= 65536) { chunk = a; min_steal = b2; }
     }
     pp.sched.ranges = ranges;
     pp.sched.n_warps = unsigned(n_warps);

@@ -33,7 +33,7 @@ struct StealParams {
     unsigned total;                 // pair steps of the launch (< 2^31)
     unsigned per_clip;              // pair steps per (full-length) clip
     unsigned chunk;                 // pairs per claim
-    unsigned min_steal;             // smallest remainder worth splitting
+    unsigned min_steal;             // smallest remainder worth splitting (>= 2: a steal takes half, rounded down)
 };
 
 B200AA_HD unsigned long long sched_pack(unsigned front, unsigned back) { return (static_cast<unsigned long long>(back) << 32) | front; }

@@ -564,7 +564,7 @@ inline int solo_launch_t(const SoloTables &stb, const StParams &p, int sm_count,
         long chunk = 8, min_steal = 2;
         if (const char *ov = getenv("B200AA_PAIR_STEAL")) {
             long a = 0, b2 = 0;
-            if (sscanf(ov, "%ld,%ld", &a, &b2) == 2 && a > 0 && b2 > 1) { chunk = a; min_steal = b2; }
+            if (sscanf(ov, "%ld,%ld", &a, &b2) == 2 && a > 0 && a <= 65536 && b2 > 1 && b2 <= 65536) { chunk = a; min_steal = b2; }
         }
         pp.sched.ranges = reinterpret_cast<unsigned long long *>(counter);
         pp.sched.n_warps = unsigned(n_warps);
