@@ -223,17 +223,58 @@ __device__ __forceinline__ void pair_spectral(const float *X, const float *Xp, f
     const float2 dstep = make_float2(2.f * invK, 2.f * invK);
     const float2 nx2 = make_float2(nx, nx), mnp2 = make_float2(-np_, -np_);
     float2 sp2 = make_float2(0.f, 0.f), fl2 = make_float2(0.f, 0.f);
-    float run = incl - part, below = 0.f;
+#ifdef B200AA_ROLLOFF_SEQ
+    float run = incl - part, below = 0.f;       // (A/B reference: every lane walks its own chunk bin by bin)
+#else
+    // rolloff = number of bins whose cumulative energy stays <= thr.  The prefix over the lanes' chunks is monotone, so the
+    // lanes before the crossing one count all their CB bins and only the crossing lane's chunk needs a bin-by-bin look: the
+    // half-warp takes it together (one or two float2 of that chunk per lane, a 4-step scan) instead of CB dependent steps per lane.
+    float below;
+    {
+        const unsigned under = __ballot_sync(0xffffffffu, incl <= thr);
+        const int cl = __popc((under >> (16 * half)) & 0xffffu);      // chunks entirely under the threshold (< 16: the last prefix is sxx > thr)
+        const float base = __shfl_sync(0xffffffffu, incl - part, cl, 16);      // cumulative energy before the crossing chunk
+        constexpr int PER = (C2 + 15) / 16;                           // float2 elements of that chunk per lane (2 for the 1024-sample window)
+        float2 sq[PER];
+        float pre = 0.f;
+#pragma unroll
+        for (int t = 0; t < PER; ++t) {
+            const int idx = l * PER + t;
+            const float2 xc = idx < C2 ? reinterpret_cast<const float2 *>(X)[cl * C2 + idx] : make_float2(0.f, 0.f);
+            sq[t] = __fmul2_rn(xc, xc);
+            pre += sq[t].x + sq[t].y;
+        }
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const float n = __shfl_up_sync(0xffffffffu, pre, o, 16);
+            if (l >= o) pre += n;
+        }
+        const float prev = __shfl_up_sync(0xffffffffu, pre, 1, 16);
+        float run = base + (l ? prev : 0.f);
+        below = 0.f;
+#pragma unroll
+        for (int t = 0; t < PER; ++t) {
+            const bool real = l * PER + t < C2;
+            run += sq[t].x;
+            below += (real && !(run > thr)) ? 1.f : 0.f;
+            run += sq[t].y;
+            below += (real && !(run > thr)) ? 1.f : 0.f;
+        }
+        if (l == 0) below += float(cl * CB);
+    }
+#endif
 #pragma unroll
     for (int j = 0; j < C2; ++j) {
         sp2 = __ffma2_rn(__fmul2_rn(d2, d2), x2[j], sp2);
         d2 = f2add(d2, dstep);
         const float2 df = __ffma2_rn(x2[j], nx2, __fmul2_rn(Xp2[j], mnp2));
         fl2 = __ffma2_rn(df, df, fl2);
+#ifdef B200AA_ROLLOFF_SEQ
         run = fmaf(x2[j].x, x2[j].x, run);
         below += run > thr ? 0.f : 1.f;
         run = fmaf(x2[j].y, x2[j].y, run);
         below += run > thr ? 0.f : 1.f;
+#endif
     }
     const float sp = sp2.x + sp2.y, fl = fl2.x + fl2.y;
     __syncwarp();
